@@ -1,0 +1,251 @@
+// Minibatch (SVI / partial_fit) kernels and small reductions of the HPF engine (sm_100a).
+// Reference semantics: hpfrec/cython_loops.pxi ("pxi") user-epoch body 275-325, item-epoch body
+// 329-377, Cython partial_fit 423-473.  "major" = the batched side, "minor" = the opposite side.
+#pragma once
+#include "hpf_device.cuh"
+
+namespace hpf {
+
+template <typename real>
+__global__ void digamma_kernel(const real* __restrict__ x, real* __restrict__ out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = digamma(x[i]);
+}
+
+// column sums (double) of a padded (nrows x ld) matrix, optionally of the elementwise ratio num/den
+template <typename real>
+__global__ void __launch_bounds__(256)
+colsum_kernel(long long nrows, int ld, int k, const real* __restrict__ num, const real* __restrict__ den,
+              double* __restrict__ out) {
+    extern __shared__ double s_col[];
+    for (int j = threadIdx.x; j < ld; j += blockDim.x) s_col[j] = 0.0;
+    __syncthreads();
+    // thread t owns column (t % ld) of rows t/ld, t/ld + rows_per_pass, ... ; blockDim is 256 and the
+    // host guarantees ld <= 256 here, wider rows loop over column tiles
+    for (int c0 = 0; c0 < ld; c0 += blockDim.x) {
+        const int rows_per_pass = (ld - c0 >= (int)blockDim.x) ? 1 : blockDim.x / (ld - c0);
+        const int width = (ld - c0 >= (int)blockDim.x) ? blockDim.x : (ld - c0);
+        const int j = c0 + threadIdx.x % width;
+        const int sub = threadIdx.x / width;
+        if (sub >= rows_per_pass || j >= k) continue;
+        double s = 0.0;
+        for (long long r = (long long)blockIdx.x * rows_per_pass + sub; r < nrows;
+             r += (long long)gridDim.x * rows_per_pass) {
+            const real v = num[r * ld + j];
+            s += den ? (double)(v / den[r * ld + j]) : (double)v;
+        }
+        atomicAdd(&s_col[j], s);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < k; j += blockDim.x) atomicAdd(out + j, s_col[j]);
+}
+
+// out[0] = sum_j a[j] * b[j]   (the all-pairs shortcut term of pxi:78)
+__global__ void dot_cols_kernel(int k, const double* __restrict__ a, const double* __restrict__ b,
+                                double* __restrict__ out) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        double s = 0.0;
+        for (int j = 0; j < k; ++j) s += a[j] * b[j];
+        out[0] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// batch prepare: for every listed row compute the softmax factor x from the CURRENT (shp, rte)
+// (what update_phi reads at pxi:292-298 / 438-440), zero the row's accumulator, stamp membership.
+// ---------------------------------------------------------------------------------------------
+template <typename real, int LPG, int VPL>
+__global__ void __launch_bounds__(256)
+batch_prepare_kernel(int nrows, const int* __restrict__ rows, int ld, int k, const real* __restrict__ shp,
+                     const real* __restrict__ rte, real* __restrict__ x, real* __restrict__ acc,
+                     int* __restrict__ stamp, int step) {
+    constexpr int EPV = Pack<real>::N;
+    const int gl = (threadIdx.x & 31) % LPG;
+    const unsigned gmask = group_mask<LPG>();
+    const int groups_per_block = blockDim.x / LPG;
+    const int g0 = blockIdx.x * groups_per_block + threadIdx.x / LPG;
+    const int gstride = gridDim.x * groups_per_block;
+    int off[VPL];
+    bool act[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        off[v] = (gl + LPG * v) * EPV;
+        act[v] = off[v] < ld;
+    }
+    for (int q = g0; q < nrows; q += gstride) {
+        const int r = rows[q];
+        Pack<real> E[VPL];
+        real m = -INFINITY;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            if (!act[v]) continue;
+            const Pack<real> sv = ld_pack(shp + (size_t)r * ld + off[v]);
+            const Pack<real> tv = ld_pack(rte + (size_t)r * ld + off[v]);
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) {
+                const real lg = (off[v] + e < k) ? digamma(sv.v[e]) - rlog(tv.v[e]) : -INFINITY;
+                E[v].v[e] = lg;
+                m = lg > m ? lg : m;
+            }
+        }
+        m = group_max<LPG>(m, gmask);
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            if (!act[v]) continue;
+            Pack<real> xn;
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) xn.v[e] = (off[v] + e < k) ? rexp(E[v].v[e] - m) : real(0);
+            st_pack(x + (size_t)r * ld + off[v], xn);
+            st_pack(acc + (size_t)r * ld + off[v], pack_zero<real>());
+        }
+        if (gl == 0) stamp[r] = step;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// major (batched) side, ALL rows:
+//   rte[r,:]  = shp_rate/rate[r] + colsum_minor            pxi:300 / 352 / 443 / 446 (full overwrite)
+//   shp[r,:]  = prior + x*acc            for batch rows     pxi:304-314 (local rows are replaced)
+//   colsum_major += shp/rte                                 (Theta.sum(axis=0) of pxi:320 / Beta.sum of 372)
+//   rate[r]   = rho*(add + sum_j shp/rte) + (1-rho)*rate[r]   batch rows (pxi:324/377) or all rows
+//                                                            when blend_all (partial_fit, pxi:472-473)
+// ---------------------------------------------------------------------------------------------
+template <typename real, int LPG, int VPL>
+__global__ void __launch_bounds__(256)
+batch_major_kernel(int nrows, int ld, int k, const real* __restrict__ x, const real* __restrict__ acc,
+                   real* __restrict__ shp, real* __restrict__ rte, real* __restrict__ rate,
+                   const int* __restrict__ stamp, int step, const double* __restrict__ colsum_minor,
+                   double* __restrict__ colsum_major, real prior, real shp_rate, real add_rate, real rho,
+                   int blend_all) {
+    constexpr int EPV = Pack<real>::N;
+    extern __shared__ double s_col[];
+    for (int j = threadIdx.x; j < ld; j += blockDim.x) s_col[j] = 0.0;
+    __syncthreads();
+    const int gl = (threadIdx.x & 31) % LPG;
+    const unsigned gmask = group_mask<LPG>();
+    const int groups_per_block = blockDim.x / LPG;
+    const int g0 = blockIdx.x * groups_per_block + threadIdx.x / LPG;
+    const int gstride = gridDim.x * groups_per_block;
+    const real prev = real(1) - rho;
+    int off[VPL];
+    bool act[VPL];
+    real other[VPL][EPV], csum[VPL][EPV];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        off[v] = (gl + LPG * v) * EPV;
+        act[v] = off[v] < ld;
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) {
+            other[v][e] = (act[v] && off[v] + e < k) ? (real)colsum_minor[off[v] + e] : real(0);
+            csum[v][e] = real(0);
+        }
+    }
+    for (int r = g0; r < nrows; r += gstride) {
+        const bool inb = stamp[r] == step;
+        const real old_rate = rate[r];
+        const real inv = shp_rate / old_rate;
+        real rowsum = real(0);
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            if (!act[v]) continue;
+            Pack<real> sv;
+            if (inb) {
+                const Pack<real> xv = ld_pack(x + (size_t)r * ld + off[v]);
+                const Pack<real> av = ld_pack(acc + (size_t)r * ld + off[v]);
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) sv.v[e] = (off[v] + e < k) ? fma(xv.v[e], av.v[e], prior) : real(0);
+                st_pack(shp + (size_t)r * ld + off[v], sv);
+            } else {
+                sv = ld_pack(shp + (size_t)r * ld + off[v]);
+            }
+            Pack<real> tv;
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) {
+                const bool real_col = off[v] + e < k;
+                tv.v[e] = real_col ? inv + other[v][e] : real(1);
+                const real th = real_col ? sv.v[e] / tv.v[e] : real(0);
+                rowsum += th;
+                csum[v][e] += th;
+            }
+            st_pack(rte + (size_t)r * ld + off[v], tv);
+        }
+        rowsum = group_sum<LPG>(rowsum, gmask);
+        if (gl == 0 && (inb || blend_all)) rate[r] = rho * (add_rate + rowsum) + prev * old_rate;
+    }
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        if (!act[v]) continue;
+#pragma unroll
+        for (int e = 0; e < EPV; ++e)
+            if (off[v] + e < k) atomicAdd(&s_col[off[v] + e], (double)csum[v][e]);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < k; j += blockDim.x) atomicAdd(colsum_major + j, s_col[j]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// minor (opposite) side; rows = the unique minor ids of the batch, or ALL rows when blend_all:
+//   batch rows:  shp = rho*mult*(prior + x*acc) + (1-rho)*shp                 pxi:316 / 368
+//                rte = rho*(shp_rate/rate[r] + colsum_major) + (1-rho)*rte    pxi:320 / 372
+//   rate[r] = rho*(add + sum_j shp/rte) + (1-rho)*rate[r]    batch rows, or all rows when blend_all
+// ---------------------------------------------------------------------------------------------
+template <typename real, int LPG, int VPL>
+__global__ void __launch_bounds__(256)
+batch_minor_kernel(int nrows, const int* __restrict__ rows, int ld, int k, const real* __restrict__ x,
+                   const real* __restrict__ acc, real* __restrict__ shp, real* __restrict__ rte,
+                   real* __restrict__ rate, const int* __restrict__ stamp, int step,
+                   const double* __restrict__ colsum_major, real prior, real shp_rate, real add_rate,
+                   real rho, real mult) {
+    constexpr int EPV = Pack<real>::N;
+    const int gl = (threadIdx.x & 31) % LPG;
+    const unsigned gmask = group_mask<LPG>();
+    const int groups_per_block = blockDim.x / LPG;
+    const int g0 = blockIdx.x * groups_per_block + threadIdx.x / LPG;
+    const int gstride = gridDim.x * groups_per_block;
+    const real prev = real(1) - rho;
+    const real rm = rho * mult;
+    int off[VPL];
+    bool act[VPL];
+    real other[VPL][EPV];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        off[v] = (gl + LPG * v) * EPV;
+        act[v] = off[v] < ld;
+#pragma unroll
+        for (int e = 0; e < EPV; ++e)
+            other[v][e] = (act[v] && off[v] + e < k) ? (real)colsum_major[off[v] + e] : real(0);
+    }
+    for (int q = g0; q < nrows; q += gstride) {
+        const int r = rows ? rows[q] : q;
+        const bool inb = rows ? true : (stamp[r] == step);
+        const real old_rate = rate[r];
+        const real inv = shp_rate / old_rate;
+        real rowsum = real(0);
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            if (!act[v]) continue;
+            Pack<real> sv = ld_pack(shp + (size_t)r * ld + off[v]);
+            Pack<real> tv = ld_pack(rte + (size_t)r * ld + off[v]);
+            if (inb) {
+                const Pack<real> xv = ld_pack(x + (size_t)r * ld + off[v]);
+                const Pack<real> av = ld_pack(acc + (size_t)r * ld + off[v]);
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) {
+                    if (off[v] + e < k) {
+                        sv.v[e] = rm * fma(xv.v[e], av.v[e], prior) + prev * sv.v[e];
+                        tv.v[e] = rho * (inv + other[v][e]) + prev * tv.v[e];
+                    }
+                }
+                st_pack(shp + (size_t)r * ld + off[v], sv);
+                st_pack(rte + (size_t)r * ld + off[v], tv);
+            }
+#pragma unroll
+            for (int e = 0; e < EPV; ++e)
+                if (off[v] + e < k) rowsum += sv.v[e] / tv.v[e];
+        }
+        rowsum = group_sum<LPG>(rowsum, gmask);
+        if (gl == 0) rate[r] = rho * (add_rate + rowsum) + prev * old_rate;
+    }
+}
+
+}  // namespace hpf

@@ -1,0 +1,134 @@
+// Device-side building blocks of the HPF engine (sm_100a): 16-byte packs, lane-group reductions,
+// digamma.  No host code here.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace hpf {
+
+// ---------------------------------------------------------------------------------------------
+// 16-byte pack of `real` (float4 / double2): every factor-row access in the engine is one 128-bit
+// load or store, rows are padded to a multiple of 32 B so a row never shares a sector.
+// ---------------------------------------------------------------------------------------------
+template <typename real>
+struct alignas(16) Pack {
+    static constexpr int N = 16 / sizeof(real);
+    real v[N];
+};
+
+template <typename real>
+__device__ __forceinline__ Pack<real> pack_zero() {
+    Pack<real> p;
+#pragma unroll
+    for (int e = 0; e < Pack<real>::N; ++e) p.v[e] = real(0);
+    return p;
+}
+
+// read-only 128-bit load (LDG.E.128.CONSTANT); data is never written by the reading kernel
+template <typename real>
+__device__ __forceinline__ Pack<real> ldg_pack(const real* p) {
+    Pack<real> r;
+    *reinterpret_cast<int4*>(&r) = __ldg(reinterpret_cast<const int4*>(p));
+    return r;
+}
+// plain 128-bit load of data this kernel may also write (no .nc)
+template <typename real>
+__device__ __forceinline__ Pack<real> ld_pack(const real* p) {
+    Pack<real> r;
+    *reinterpret_cast<int4*>(&r) = *reinterpret_cast<const int4*>(p);
+    return r;
+}
+template <typename real>
+__device__ __forceinline__ void st_pack(real* p, const Pack<real>& r) {
+    *reinterpret_cast<int4*>(p) = *reinterpret_cast<const int4*>(&r);
+}
+
+// vector reduction into global memory: RED.E.ADD.F32x4 (sm_90+) for float, 2x RED.E.ADD.F64 for double
+__device__ __forceinline__ void red_add_pack(float* p, const Pack<float>& r) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]),
+                 "f"(r.v[2]), "f"(r.v[3])
+                 : "memory");
+}
+__device__ __forceinline__ void red_add_pack(double* p, const Pack<double>& r) {
+    atomicAdd(p, r.v[0]);
+    atomicAdd(p + 1, r.v[1]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// lane groups: LPG consecutive lanes of a warp own one factor row; lane gl holds packs
+// gl, gl+LPG, ... (VPL of them) so that one load instruction of the group covers LPG*16 contiguous bytes.
+// ---------------------------------------------------------------------------------------------
+template <int LPG>
+__device__ __forceinline__ unsigned group_mask() {
+    if constexpr (LPG == 32) {
+        return 0xffffffffu;
+    } else {
+        const unsigned lane = threadIdx.x & 31u;
+        return ((1u << LPG) - 1u) << (lane & ~(unsigned)(LPG - 1));
+    }
+}
+template <int LPG, typename T>
+__device__ __forceinline__ T group_sum(T x, unsigned mask) {
+#pragma unroll
+    for (int o = LPG / 2; o > 0; o >>= 1) x += __shfl_xor_sync(mask, x, o, LPG);
+    return x;
+}
+template <int LPG, typename T>
+__device__ __forceinline__ T group_max(T x, unsigned mask) {
+#pragma unroll
+    for (int o = LPG / 2; o > 0; o >>= 1) {
+        T y = __shfl_xor_sync(mask, x, o, LPG);
+        x = x > y ? x : y;
+    }
+    return x;
+}
+
+// ---------------------------------------------------------------------------------------------
+// math
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rlog(float x) { return logf(x); }
+__device__ __forceinline__ double rlog(double x) { return log(x); }
+__device__ __forceinline__ float rexp(float x) { return expf(x); }
+__device__ __forceinline__ double rexp(double x) { return exp(x); }
+// count / normaliser: 2-ulp MUFU division is ample for float (parity gate 1e-5), IEEE for double
+__device__ __forceinline__ float rdiv_fast(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ double rdiv_fast(double a, double b) { return a / b; }
+
+// digamma for x > 0.  The reference calls scipy.special.cython_special.psi (pxi:5, call sites
+// pxi:570/588/685/717), i.e. cephes `psi`: upward recurrence psi(x) = psi(x+1) - 1/x until x >= 10,
+// then the asymptotic series log(x) - 1/(2x) - sum_n B_2n / (2n x^2n).  Same scheme here (7 Bernoulli
+// terms in double; in float the shift target is 6 and 3 terms already reach 1 ulp).  Validated
+// against scipy on a dense grid in tests/test_digamma.py.
+__device__ __forceinline__ double digamma(double x) {
+    double acc = 0.0;
+    while (x < 10.0) {
+        acc -= 1.0 / x;
+        x += 1.0;
+    }
+    const double r = 1.0 / x;
+    const double r2 = r * r;
+    double p = 8.33333333333333333333e-2;               //  1/12   (x^-14)
+    p = fma(p, r2, -2.10927960927960927961e-2);         // -691/32760
+    p = fma(p, r2, 7.57575757575757575758e-3);          //  1/132
+    p = fma(p, r2, -4.16666666666666666667e-3);         // -1/240
+    p = fma(p, r2, 3.96825396825396825397e-3);          //  1/252
+    p = fma(p, r2, -8.33333333333333333333e-3);         // -1/120
+    p = fma(p, r2, 8.33333333333333333333e-2);          //  1/12   (x^-2)
+    return acc + (log(x) - 0.5 * r - r2 * p);
+}
+__device__ __forceinline__ float digamma(float x) {
+    float acc = 0.0f;
+    while (x < 6.0f) {
+        acc -= __frcp_rn(x);
+        x += 1.0f;
+    }
+    const float r = __frcp_rn(x);
+    const float r2 = r * r;
+    float p = 3.96825396825396825397e-3f;
+    p = fmaf(p, r2, -8.33333333333333333333e-3f);
+    p = fmaf(p, r2, 8.33333333333333333333e-2f);
+    return acc + (logf(x) - 0.5f * r - r2 * p);
+}
+
+}  // namespace hpf

@@ -1,0 +1,1020 @@
+// Host side of the HPF engine + the extern "C" boundary declared in include/hpf_b200.h.
+// Built by hpfrec_b200/build.py:  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -shared ...
+// No torch, no CPU compute path: every entry point either runs CUDA kernels or fails with a code.
+#include "../../include/hpf_b200.h"
+#include "hpf_kernels.cuh"
+#include "hpf_batch.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(e_ == cudaErrorMemoryAllocation ? HPF_ENOMEM : HPF_ECUDA, "%s failed: %s (%s:%d)", \
+                        #call, cudaGetErrorString(e_), __FILE__, __LINE__);                        \
+    } while (0)
+#define CKK() CK(cudaGetLastError())
+#define TRY(expr)                      \
+    do {                               \
+        int rc_ = (expr);              \
+        if (rc_ != HPF_OK) return rc_; \
+    } while (0)
+
+template <typename real_, int LPG, int VPL>
+struct Cfg {
+    using real = real_;
+    static constexpr int lpg = LPG, vpl = VPL;
+};
+
+// lane-group shape from the padded row length (16-byte packs per row)
+template <typename F>
+int dispatch(int real_bytes, int ld, F&& f) {
+    const int packs = ld * real_bytes / 16;
+    if (real_bytes == 4) {
+        if (packs <= 8) return f(Cfg<float, 8, 1>{});
+        if (packs <= 16) return f(Cfg<float, 8, 2>{});
+        if (packs <= 32) return f(Cfg<float, 16, 2>{});
+        if (packs <= 64) return f(Cfg<float, 32, 2>{});
+        if (packs <= 128) return f(Cfg<float, 32, 4>{});
+    } else if (real_bytes == 8) {
+        if (packs <= 8) return f(Cfg<double, 8, 1>{});
+        if (packs <= 16) return f(Cfg<double, 8, 2>{});
+        if (packs <= 32) return f(Cfg<double, 16, 2>{});
+        if (packs <= 64) return f(Cfg<double, 32, 2>{});
+        if (packs <= 128) return f(Cfg<double, 32, 4>{});
+    }
+    return fail(HPF_EINVAL, "unsupported row length: k too large for this build (ld=%d, real_bytes=%d)", ld,
+                real_bytes);
+}
+
+bool is_device_ptr(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+inline unsigned nblk(long long n, int t = 256) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace
+
+// -------------------------------------------------------------------------------------------------
+struct hpf_engine {
+    int device = 0;
+    int64_t nU = 0, nI = 0;
+    int k = 0, ld = 0, rb = 4;
+    cudaStream_t stream = nullptr;
+    // constants of the updates, already rounded to `real` the way the reference's typed locals are
+    // (cdef real_t k_shp = a_prime + k*a, pxi:173-174; add_k_rte = a_prime/b_prime, pxi:209-210)
+    double a = 0.3, c = 0.3, k_shp = 0.0, t_shp = 0.0, add_k = 0.3, add_t = 0.3;
+    // variational state, padded (n x ld)
+    void *Gshp = nullptr, *Grte = nullptr, *Lshp = nullptr, *Lrte = nullptr, *krte = nullptr, *trte = nullptr;
+    // engine-private: per-row softmax factors and sweep accumulators
+    void *xu = nullptr, *xi = nullptr, *accU = nullptr, *accI = nullptr;
+    double *Tsum = nullptr, *Bsum = nullptr;  // column sums of Theta / Beta (ld doubles each)
+    bool state_loaded = false;
+    bool x_valid = false;    // xu/xi/Bsum consistent with (shp, rte) and acc buffers zero
+    bool mat_valid = false;  // Gshp/Grte/Lshp/Lrte hold the current state
+    // data: two orderings of the same triples
+    int64_t nnz = 0;
+    int *A_row = nullptr, *A_col = nullptr;  // user-major: row = user, col = item
+    void* A_val = nullptr;
+    int *B_row = nullptr, *B_col = nullptr;  // item-major: row = item, col = user
+    void* B_val = nullptr;
+    bool data_loaded = false;
+    // options
+    double panel_mb = 48.0;
+    int chunk = 128;
+    int sweep_mode = 0;
+    int use_graph = 0;
+    int64_t launches = 0;
+    cudaGraphExec_t graph_lean = nullptr, graph_mat = nullptr;
+    // optional per-kernel timing of full-batch iterations
+    int timing = 0;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    double phase_ms[4] = {0, 0, 0, 0};
+    int64_t phase_iters = 0;
+    // minibatch membership stamps (allocated at the first hpf_step_batch)
+    int *stamp_u = nullptr, *stamp_i = nullptr;
+    int batch_step = 0;
+
+    size_t mat_bytes(int64_t n) const { return (size_t)n * ld * rb; }
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = 0;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        want = dev;
+    }
+    ~DeviceGuard() {
+        if (prev != want) cudaSetDevice(prev);
+    }
+    int want;
+};
+
+int free_data(hpf_engine* h) {
+    cudaFree(h->A_row);
+    cudaFree(h->A_col);
+    cudaFree(h->A_val);
+    cudaFree(h->B_row);
+    cudaFree(h->B_col);
+    cudaFree(h->B_val);
+    h->A_row = h->A_col = h->B_row = h->B_col = nullptr;
+    h->A_val = h->B_val = nullptr;
+    h->data_loaded = false;
+    h->nnz = 0;
+    return HPF_OK;
+}
+
+void drop_graphs(hpf_engine* h) {
+    if (h->graph_lean) cudaGraphExecDestroy(h->graph_lean);
+    if (h->graph_mat) cudaGraphExecDestroy(h->graph_mat);
+    h->graph_lean = h->graph_mat = nullptr;
+}
+
+// Stages a caller buffer ([h|d]) on the device.  Returns the device pointer to read from and, if a
+// staging copy was made, the allocation to free afterwards.
+int stage_in(hpf_engine* h, const void* src, size_t bytes, const void** dev, void** to_free) {
+    *to_free = nullptr;
+    if (bytes == 0 || is_device_ptr(src)) {
+        *dev = src;
+        return HPF_OK;
+    }
+    void* tmp = nullptr;
+    CK(cudaMalloc(&tmp, bytes));
+    cudaError_t e = cudaMemcpyAsync(tmp, src, bytes, cudaMemcpyHostToDevice, h->stream);
+    if (e != cudaSuccess) {
+        cudaFree(tmp);
+        return fail(HPF_ECUDA, "H2D copy failed: %s", cudaGetErrorString(e));
+    }
+    *dev = tmp;
+    *to_free = tmp;
+    return HPF_OK;
+}
+
+// caller index array ([h|d], 4 or 8 bytes per entry) -> validated int32 device array
+int stage_index(hpf_engine* h, const void* src, int64_t n, int index_bytes, int64_t limit, int* out,
+                int* d_bad) {
+    const void* dev;
+    void* tmp;
+    TRY(stage_in(h, src, (size_t)n * index_bytes, &dev, &tmp));
+    if (n > 0) {
+        if (index_bytes == 8)
+            hpf::convert_index_kernel<long long><<<nblk(n), 256, 0, h->stream>>>((const long long*)dev, out, n, limit, d_bad);
+        else
+            hpf::convert_index_kernel<int><<<nblk(n), 256, 0, h->stream>>>((const int*)dev, out, n, limit, d_bad);
+        h->launches++;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (tmp) {
+        cudaStreamSynchronize(h->stream);
+        cudaFree(tmp);
+    }
+    if (e != cudaSuccess) return fail(HPF_ECUDA, "index conversion failed: %s", cudaGetErrorString(e));
+    return HPF_OK;
+}
+
+template <typename real>
+int upload_matrix(hpf_engine* h, const void* src, void* dst, int64_t nrows, int k, int ld, real fill) {
+    const void* dev;
+    void* tmp;
+    TRY(stage_in(h, src, (size_t)nrows * k * sizeof(real), &dev, &tmp));
+    if (nrows > 0) {
+        hpf::pad_rows_kernel<real><<<nblk(nrows * ld), 256, 0, h->stream>>>((const real*)dev, (real*)dst, nrows, k, ld, fill);
+        h->launches++;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (tmp) {
+        cudaStreamSynchronize(h->stream);
+        cudaFree(tmp);
+    }
+    if (e != cudaSuccess) return fail(HPF_ECUDA, "pad_rows failed: %s", cudaGetErrorString(e));
+    return HPF_OK;
+}
+
+// padded engine matrix (optionally divided elementwise by `denom`) -> caller buffer [h|d]
+template <typename real>
+int download_matrix(hpf_engine* h, const void* src, const void* denom, void* dst, int64_t nrows, int k,
+                    int ld) {
+    if (dst == nullptr || nrows == 0) return HPF_OK;
+    const size_t bytes = (size_t)nrows * k * sizeof(real);
+    const bool dev_dst = is_device_ptr(dst);
+    void* tmp = nullptr;
+    real* out = (real*)dst;
+    if (!dev_dst) {
+        CK(cudaMalloc(&tmp, bytes));
+        out = (real*)tmp;
+    }
+    hpf::unpad_rows_kernel<real><<<nblk(nrows * k), 256, 0, h->stream>>>((const real*)src, (const real*)denom, out, nrows, k, ld);
+    h->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && !dev_dst) e = cudaMemcpyAsync(dst, tmp, bytes, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (tmp) cudaFree(tmp);
+    if (e != cudaSuccess) return fail(HPF_ECUDA, "export failed: %s", cudaGetErrorString(e));
+    return HPF_OK;
+}
+
+// ---- ordering build: sort triples by (panel of minor id, major id) ---------------------------------
+template <typename real>
+int build_order(hpf_engine* h, const int* major, const int* minor, const real* val, int64_t n,
+                int64_t n_major, int64_t n_minor, int** o_row, int** o_col, void** o_val) {
+    CK(cudaMalloc(o_row, sizeof(int) * (size_t)(n > 0 ? n : 1)));
+    CK(cudaMalloc(o_col, sizeof(int) * (size_t)(n > 0 ? n : 1)));
+    CK(cudaMalloc(o_val, sizeof(real) * (size_t)(n > 0 ? n : 1)));
+    if (n == 0) return HPF_OK;
+    // panels: the gathered (minor) factor matrix is cut so one panel stays L2-resident
+    const double minor_bytes = (double)n_minor * h->ld * h->rb;
+    int panels = (int)((minor_bytes + h->panel_mb * 1048576.0 - 1.0) / (h->panel_mb * 1048576.0));
+    if (panels < 1) panels = 1;
+    const int per_panel = (int)((n_minor + panels - 1) / panels);
+    const unsigned long long span = (unsigned long long)(n_major > 0 ? n_major : 1);
+    int end_bit = 1;
+    while (end_bit < 64 && ((unsigned long long)panels * span - 1ull) >> end_bit) ++end_bit;
+
+    unsigned long long *k_in = nullptr, *k_out = nullptr;
+    unsigned *p_in = nullptr, *p_out = nullptr;
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    int rc = HPF_OK;
+    cudaError_t e;
+#define OCK(call)                                                                        \
+    if (rc == HPF_OK && (e = (call)) != cudaSuccess)                                     \
+    rc = fail(e == cudaErrorMemoryAllocation ? HPF_ENOMEM : HPF_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e))
+    OCK(cudaMalloc(&k_in, 8 * (size_t)n));
+    OCK(cudaMalloc(&k_out, 8 * (size_t)n));
+    OCK(cudaMalloc(&p_in, 4 * (size_t)n));
+    OCK(cudaMalloc(&p_out, 4 * (size_t)n));
+    if (rc == HPF_OK) {
+        hpf::make_keys_kernel<<<nblk(n), 256, 0, h->stream>>>(major, minor, n, per_panel, span, k_in, p_in);
+        h->launches++;
+    }
+    OCK(cudaGetLastError());
+    OCK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, p_in, p_out, (int)n, 0, end_bit, h->stream));
+    OCK(cudaMalloc(&tmp, tmp_bytes > 0 ? tmp_bytes : 16));
+    OCK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, p_in, p_out, (int)n, 0, end_bit, h->stream));
+    if (rc == HPF_OK) {
+        hpf::apply_order_kernel<real><<<nblk(n), 256, 0, h->stream>>>(k_out, p_out, n, span, minor, val, *o_row, *o_col, (real*)*o_val);
+        h->launches += 4;
+    }
+    OCK(cudaGetLastError());
+    OCK(cudaStreamSynchronize(h->stream));
+#undef OCK
+    cudaFree(k_in);
+    cudaFree(k_out);
+    cudaFree(p_in);
+    cudaFree(p_out);
+    cudaFree(tmp);
+    return rc;
+}
+
+// ---- kernel launch wrappers -----------------------------------------------------------------------
+template <typename C>
+int launch_sweep_major(hpf_engine* h, const int* row, const int* col, const void* val, const void* xown,
+                       const void* xgat, void* acc) {
+    using real = typename C::real;
+    if (h->nnz == 0) return HPF_OK;
+    const long long groups = (h->nnz + h->chunk - 1) / h->chunk;
+    const long long threads = groups * C::lpg;
+    constexpr int UNROLL = 4;
+    hpf::sweep_major_kernel<real, C::lpg, C::vpl, UNROLL><<<nblk(threads), 256, 0, h->stream>>>(
+        row, col, (const real*)val, h->nnz, h->chunk, (const real*)xown, (const real*)xgat, (real*)acc, h->ld);
+    h->launches++;
+    CKK();
+    return HPF_OK;
+}
+
+template <typename C>
+int launch_sweep_coo(hpf_engine* h, const int* iu, const int* ii, const void* val, int64_t n, const void* xu,
+                     const void* xi, void* accU, void* accI, int ld, void* phi, int k, cudaStream_t st) {
+    using real = typename C::real;
+    if (n == 0) return HPF_OK;
+    const int chunk = 64;
+    const long long groups = (n + chunk - 1) / chunk;
+    hpf::sweep_coo_kernel<real, C::lpg, C::vpl><<<nblk(groups * C::lpg), 256, 0, st>>>(
+        iu, ii, (const real*)val, n, chunk, (const real*)xu, (const real*)xi, (real*)accU, (real*)accI, ld,
+        (real*)phi, k);
+    if (h) h->launches++;
+    CKK();
+    return HPF_OK;
+}
+
+int row_grid(int64_t nrows, int lpg) {
+    const int gpb = 256 / lpg;
+    long long want = (nrows + gpb - 1) / gpb;
+    const long long cap = 148 * 8;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    return (int)want;
+}
+
+template <typename C>
+int launch_update_rows(hpf_engine* h, bool users, bool mat) {
+    using real = typename C::real;
+    const int64_t n = users ? h->nU : h->nI;
+    if (n == 0) return HPF_OK;
+    const int grid = row_grid(n, C::lpg);
+    const size_t smem = sizeof(double) * h->ld;
+    real* x = (real*)(users ? h->xu : h->xi);
+    real* acc = (real*)(users ? h->accU : h->accI);
+    real* shp = (real*)(users ? h->Gshp : h->Lshp);
+    real* rte = (real*)(users ? h->Grte : h->Lrte);
+    real* rate = (real*)(users ? h->krte : h->trte);
+    const double* other = users ? h->Bsum : h->Tsum;
+    double* out = users ? h->Tsum : h->Bsum;
+    const real prior = (real)(users ? h->a : h->c);
+    const real shp_rate = (real)(users ? h->k_shp : h->t_shp);
+    const real add_rate = (real)(users ? h->add_k : h->add_t);
+    if (mat)
+        hpf::update_rows_kernel<real, C::lpg, C::vpl, true><<<grid, 256, smem, h->stream>>>(
+            (int)n, h->ld, h->k, x, acc, shp, rte, rate, other, out, prior, shp_rate, add_rate);
+    else
+        hpf::update_rows_kernel<real, C::lpg, C::vpl, false><<<grid, 256, smem, h->stream>>>(
+            (int)n, h->ld, h->k, x, acc, shp, rte, rate, other, out, prior, shp_rate, add_rate);
+    h->launches++;
+    CKK();
+    return HPF_OK;
+}
+
+template <typename C>
+int launch_rows_to_x(hpf_engine* h, int64_t nrows, const int* rows, const void* shp, const void* rte, void* x,
+                     double* colsum, int ld, int k, cudaStream_t st) {
+    using real = typename C::real;
+    if (nrows == 0) return HPF_OK;
+    hpf::rows_to_x_kernel<real, C::lpg, C::vpl><<<row_grid(nrows, C::lpg), 256, sizeof(double) * ld, st>>>(
+        (int)nrows, rows, ld, k, (const real*)shp, (const real*)rte, (real*)x, colsum);
+    if (h) h->launches++;
+    CKK();
+    return HPF_OK;
+}
+
+// make xu/xi/Bsum consistent with the materialised state and zero the accumulators
+int ensure_x(hpf_engine* h) {
+    if (h->x_valid) return HPF_OK;
+    if (!h->state_loaded) return fail(HPF_ESTATE, "no state loaded (call hpf_load_state first)");
+    CK(cudaMemsetAsync(h->Bsum, 0, sizeof(double) * h->ld, h->stream));
+    CK(cudaMemsetAsync(h->accU, 0, h->mat_bytes(h->nU), h->stream));
+    CK(cudaMemsetAsync(h->accI, 0, h->mat_bytes(h->nI), h->stream));
+    TRY(dispatch(h->rb, h->ld, [&](auto cfg) {
+        using C = decltype(cfg);
+        TRY(launch_rows_to_x<C>(h, h->nU, nullptr, h->Gshp, h->Grte, h->xu, nullptr, h->ld, h->k, h->stream));
+        TRY(launch_rows_to_x<C>(h, h->nI, nullptr, h->Lshp, h->Lrte, h->xi, h->Bsum, h->ld, h->k, h->stream));
+        return HPF_OK;
+    }));
+    h->x_valid = true;
+    return HPF_OK;
+}
+
+// phase marks for the optional per-kernel timing ("timing" option): 0 start, 1 after pass B,
+// 2 after pass A, 3 after the user update, 4 after the item update
+void mark(hpf_engine* h, int which) {
+    if (h->timing && h->ev[0]) cudaEventRecord(h->ev[which], h->stream);
+}
+
+int do_sweep(hpf_engine* h) {
+    return dispatch(h->rb, h->ld, [&](auto cfg) {
+        using C = decltype(cfg);
+        mark(h, 0);
+        if (h->sweep_mode == 1) {
+            TRY(launch_sweep_coo<C>(h, h->A_row, h->A_col, h->A_val, h->nnz, h->xu, h->xi, h->accU, h->accI,
+                                    h->ld, nullptr, h->k, h->stream));
+            mark(h, 1);
+            mark(h, 2);
+            return HPF_OK;
+        }
+        // pass B first: its output (item-side partial sums) is what a multi-GPU caller all-reduces,
+        // so the reduction can overlap pass A
+        TRY(launch_sweep_major<C>(h, h->B_row, h->B_col, h->B_val, h->xi, h->xu, h->accI));
+        mark(h, 1);
+        TRY(launch_sweep_major<C>(h, h->A_row, h->A_col, h->A_val, h->xu, h->xi, h->accU));
+        mark(h, 2);
+        return HPF_OK;
+    });
+}
+
+int do_update(hpf_engine* h, bool users, bool mat) {
+    // the side being updated accumulates its column sums into a zeroed buffer
+    CK(cudaMemsetAsync(users ? h->Tsum : h->Bsum, 0, sizeof(double) * h->ld, h->stream));
+    return dispatch(h->rb, h->ld, [&](auto cfg) {
+        using C = decltype(cfg);
+        return launch_update_rows<C>(h, users, mat);
+    });
+}
+
+int one_iteration(hpf_engine* h, bool mat) {
+    TRY(do_sweep(h));
+    TRY(do_update(h, true, mat));
+    mark(h, 3);
+    TRY(do_update(h, false, mat));
+    mark(h, 4);
+    if (h->timing && h->ev[0]) {  // profiling mode only: serialises iterations
+        CK(cudaEventSynchronize(h->ev[4]));
+        for (int p = 0; p < 4; ++p) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, h->ev[p], h->ev[p + 1]));
+            h->phase_ms[p] += ms;
+        }
+        h->phase_iters++;
+    }
+    return HPF_OK;
+}
+
+int capture_iteration(hpf_engine* h, bool mat, cudaGraphExec_t* out) {
+    cudaGraph_t g = nullptr;
+    cudaStream_t cs = h->stream;
+    cudaStream_t own = nullptr;
+    if (cs == nullptr || cs == cudaStreamLegacy) {  // the legacy stream cannot be captured
+        CK(cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking));
+        cs = own;
+    }
+    cudaStream_t saved = h->stream;
+    h->stream = cs;
+    int64_t l0 = h->launches;
+    cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+    int rc = HPF_OK;
+    if (e == cudaSuccess) {
+        rc = one_iteration(h, mat);
+        cudaError_t e2 = cudaStreamEndCapture(cs, &g);
+        if (rc == HPF_OK && e2 != cudaSuccess) rc = fail(HPF_ECUDA, "graph capture failed: %s", cudaGetErrorString(e2));
+    } else {
+        rc = fail(HPF_ECUDA, "cudaStreamBeginCapture failed: %s", cudaGetErrorString(e));
+    }
+    h->launches = l0;
+    h->stream = saved;
+    if (rc == HPF_OK) {
+        e = cudaGraphInstantiate(out, g, 0);
+        if (e != cudaSuccess) rc = fail(HPF_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    }
+    if (g) cudaGraphDestroy(g);
+    if (own) cudaStreamDestroy(own);
+    return rc;
+}
+
+constexpr int kLaunchesPerIteration = 4;  // 2 sweep passes + 2 row updates (memsets not counted)
+
+}  // namespace
+
+// =================================================================================================
+// extern "C"
+// =================================================================================================
+extern "C" {
+
+int hpf_abi_version(void) { return 1; }
+const char* hpf_last_error(void) { return g_err.c_str(); }
+
+int hpf_create(hpf_engine** out, int64_t nU, int64_t nI, int32_t k, int32_t real_bytes, int32_t device) {
+    if (!out) return fail(HPF_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (nU < 0 || nI < 0 || k <= 0) return fail(HPF_EINVAL, "bad shape nU=%lld nI=%lld k=%d", (long long)nU, (long long)nI, k);
+    if (nU >= (1ll << 31) || nI >= (1ll << 31)) return fail(HPF_EINVAL, "row counts must be < 2^31");
+    if (real_bytes != 4 && real_bytes != 8) return fail(HPF_EINVAL, "real_bytes must be 4 or 8");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(HPF_ECUDA, "no CUDA device available (this engine has no CPU path)");
+    }
+    if (device < 0 || device >= ndev) return fail(HPF_EINVAL, "device %d out of range (%d devices)", device, ndev);
+    DeviceGuard guard(device);
+    const int per32 = 32 / real_bytes;  // rows padded to whole 32-byte sectors
+    const int ld = (k + per32 - 1) / per32 * per32;
+    TRY(dispatch(real_bytes, ld, [](auto) { return HPF_OK; }));
+    hpf_engine* h = new hpf_engine();
+    h->device = device;
+    h->nU = nU;
+    h->nI = nI;
+    h->k = k;
+    h->ld = ld;
+    h->rb = real_bytes;
+    hpf_set_hyper(h, 0.3, 0.3, 1.0, 0.3, 0.3, 1.0);  // the reference's defaults (hpfrec/__init__.py:205-206)
+    const size_t mu = h->mat_bytes(nU > 0 ? nU : 1), mi = h->mat_bytes(nI > 0 ? nI : 1);
+    cudaError_t e = cudaSuccess;
+    void** mats_u[] = {&h->Gshp, &h->Grte, &h->xu, &h->accU};
+    void** mats_i[] = {&h->Lshp, &h->Lrte, &h->xi, &h->accI};
+    for (auto p : mats_u)
+        if (e == cudaSuccess) e = cudaMalloc(p, mu);
+    for (auto p : mats_i)
+        if (e == cudaSuccess) e = cudaMalloc(p, mi);
+    if (e == cudaSuccess) e = cudaMalloc(&h->krte, (size_t)(nU > 0 ? nU : 1) * real_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&h->trte, (size_t)(nI > 0 ? nI : 1) * real_bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&h->Tsum, sizeof(double) * ld);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&h->Bsum, sizeof(double) * ld);
+    if (e == cudaSuccess) e = cudaMemset(h->Tsum, 0, sizeof(double) * ld);
+    if (e == cudaSuccess) e = cudaMemset(h->Bsum, 0, sizeof(double) * ld);
+    if (e != cudaSuccess) {
+        int rc = fail(e == cudaErrorMemoryAllocation ? HPF_ENOMEM : HPF_ECUDA, "device allocation failed: %s", cudaGetErrorString(e));
+        hpf_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return HPF_OK;
+}
+
+int hpf_destroy(hpf_engine* h) {
+    if (!h) return HPF_OK;
+    DeviceGuard guard(h->device);
+    cudaDeviceSynchronize();
+    drop_graphs(h);
+    free_data(h);
+    for (auto e : h->ev)
+        if (e) cudaEventDestroy(e);
+    void* ptrs[] = {h->Gshp, h->Grte, h->Lshp, h->Lrte, h->krte, h->trte, h->xu, h->xi, h->accU, h->accI, h->Tsum, h->Bsum, h->stamp_u, h->stamp_i};
+    for (void* p : ptrs) cudaFree(p);
+    delete h;
+    return HPF_OK;
+}
+
+int hpf_set_hyper(hpf_engine* h, double a, double a_prime, double b_prime, double c, double c_prime, double d_prime) {
+    if (!h) return fail(HPF_EINVAL, "engine is NULL");
+    if (!(a > 0 && a_prime > 0 && b_prime > 0 && c > 0 && c_prime > 0 && d_prime > 0))
+        return fail(HPF_EINVAL, "hyper-parameters must be positive");
+    if (h->rb == 4) {
+        const float af = (float)a, apf = (float)a_prime, bpf = (float)b_prime, cf = (float)c, cpf = (float)c_prime, dpf = (float)d_prime;
+        h->a = af;
+        h->c = cf;
+        h->k_shp = (float)(apf + (float)h->k * af);
+        h->t_shp = (float)(cpf + (float)h->k * cf);
+        h->add_k = (float)(apf / bpf);
+        h->add_t = (float)(cpf / dpf);
+    } else {
+        h->a = a;
+        h->c = c;
+        h->k_shp = a_prime + (double)h->k * a;
+        h->t_shp = c_prime + (double)h->k * c;
+        h->add_k = a_prime / b_prime;
+        h->add_t = c_prime / d_prime;
+    }
+    drop_graphs(h);
+    return HPF_OK;
+}
+
+int hpf_set_constants(hpf_engine* h, double a, double c, double k_shp, double t_shp, double add_k_rte, double add_t_rte) {
+    if (!h) return fail(HPF_EINVAL, "engine is NULL");
+    if (!(a > 0 && c > 0 && k_shp > 0 && t_shp > 0 && add_k_rte > 0 && add_t_rte > 0))
+        return fail(HPF_EINVAL, "constants must be positive");
+    h->a = a;
+    h->c = c;
+    h->k_shp = k_shp;
+    h->t_shp = t_shp;
+    h->add_k = add_k_rte;
+    h->add_t = add_t_rte;
+    drop_graphs(h);
+    return HPF_OK;
+}
+
+int hpf_set_stream(hpf_engine* h, void* cuda_stream) {
+    if (!h) return fail(HPF_EINVAL, "engine is NULL");
+    h->stream = (cudaStream_t)cuda_stream;
+    return HPF_OK;
+}
+
+int hpf_set_option(hpf_engine* h, const char* name, double value) {
+    if (!h || !name) return fail(HPF_EINVAL, "engine or name is NULL");
+    if (!strcmp(name, "panel_mb")) {
+        if (!(value > 0)) return fail(HPF_EINVAL, "panel_mb must be > 0");
+        h->panel_mb = value;  // takes effect at the next hpf_load_coo
+    } else if (!strcmp(name, "chunk")) {
+        if (value < 1 || value > (1 << 20)) return fail(HPF_EINVAL, "chunk out of range");
+        h->chunk = (int)value;
+        drop_graphs(h);
+    } else if (!strcmp(name, "sweep")) {
+        h->sweep_mode = (int)value;
+        drop_graphs(h);
+    } else if (!strcmp(name, "use_graph")) {
+        h->use_graph = (int)value;
+    } else if (!strcmp(name, "timing")) {
+        h->timing = (int)value;
+        if (h->timing && !h->ev[0]) {
+            DeviceGuard guard(h->device);
+            for (auto& e : h->ev) CK(cudaEventCreate(&e));
+        }
+        for (double& v : h->phase_ms) v = 0.0;
+        h->phase_iters = 0;
+    } else {
+        return fail(HPF_EINVAL, "unknown option '%s'", name);
+    }
+    return HPF_OK;
+}
+
+int hpf_load_state(hpf_engine* h, const void* Gamma_shp, const void* Gamma_rte, const void* Lambda_shp,
+                   const void* Lambda_rte, const void* k_rte, const void* t_rte) {
+    if (!h) return fail(HPF_EINVAL, "engine is NULL");
+    if (!Gamma_shp || !Gamma_rte || !Lambda_shp || !Lambda_rte || !k_rte || !t_rte)
+        return fail(HPF_EINVAL, "all six state arrays are required");
+    DeviceGuard guard(h->device);
+    auto up = [&](auto one) {
+        using real = decltype(one);
+        TRY(upload_matrix<real>(h, Gamma_shp, h->Gshp, h->nU, h->k, h->ld, real(0)));
+        TRY(upload_matrix<real>(h, Gamma_rte, h->Grte, h->nU, h->k, h->ld, real(1)));
+        TRY(upload_matrix<real>(h, Lambda_shp, h->Lshp, h->nI, h->k, h->ld, real(0)));
+        TRY(upload_matrix<real>(h, Lambda_rte, h->Lrte, h->nI, h->k, h->ld, real(1)));
+        return HPF_OK;
+    };
+    TRY(h->rb == 4 ? up(0.0f) : up(0.0));
+    CK(cudaMemcpyAsync(h->krte, k_rte, (size_t)h->nU * h->rb, cudaMemcpyDefault, h->stream));
+    CK(cudaMemcpyAsync(h->trte, t_rte, (size_t)h->nI * h->rb, cudaMemcpyDefault, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->state_loaded = true;
+    h->mat_valid = true;
+    h->x_valid = false;
+    return HPF_OK;
+}
+
+int hpf_export_state(hpf_engine* h, void* Gamma_shp, void* Gamma_rte, void* Lambda_shp, void* Lambda_rte,
+                     void* k_rte, void* t_rte, void* Theta, void* Beta) {
+    if (!h) return fail(HPF_EINVAL, "engine is NULL");
+    if (!h->state_loaded) return fail(HPF_ESTATE, "no state loaded");
+    if (!h->mat_valid) return fail(HPF_ESTATE, "internal: state matrices not materialised");
+    DeviceGuard guard(h->device);
+    auto down = [&](auto one) {
+        using real = decltype(one);
+        TRY(download_matrix<real>(h, h->Gshp, nullptr, Gamma_shp, h->nU, h->k, h->ld));
+        TRY(download_matrix<real>(h, h->Grte, nullptr, Gamma_rte, h->nU, h->k, h->ld));
+        TRY(download_matrix<real>(h, h->Lshp, nullptr, Lambda_shp, h->nI, h->k, h->ld));
+        TRY(download_matrix<real>(h, h->Lrte, nullptr, Lambda_rte, h->nI, h->k, h->ld));
+        TRY(download_matrix<real>(h, h->Gshp, h->Grte, Theta, h->nU, h->k, h->ld));
+        TRY(download_matrix<real>(h, h->Lshp, h->Lrte, Beta, h->nI, h->k, h->ld));
+        return HPF_OK;
+    };
+    TRY(h->rb == 4 ? down(0.0f) : down(0.0));
+    if (k_rte) CK(cudaMemcpyAsync(k_rte, h->krte, (size_t)h->nU * h->rb, cudaMemcpyDefault, h->stream));
+    if (t_rte) CK(cudaMemcpyAsync(t_rte, h->trte, (size_t)h->nI * h->rb, cudaMemcpyDefault, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return HPF_OK;
+}
+
+int hpf_load_coo(hpf_engine* h, const void* ix_u, const void* ix_i, const void* Y, int64_t nnz, int32_t index_bytes) {
+    if (!h) return fail(HPF_EINVAL, "engine is NULL");
+    if (nnz < 0 || nnz >= (1ll << 31)) return fail(HPF_EINVAL, "nnz must be in [0, 2^31)");
+    if (index_bytes != 4 && index_bytes != 8) return fail(HPF_EINVAL, "index_bytes must be 4 or 8");
+    if (nnz > 0 && (!ix_u || !ix_i || !Y)) return fail(HPF_EINVAL, "NULL triple array");
+    DeviceGuard guard(h->device);
+    drop_graphs(h);
+    free_data(h);
+    h->nnz = nnz;
+    int *u32 = nullptr, *i32 = nullptr, *d_bad = nullptr;
+    void* to_free = nullptr;
+    const void* yv = nullptr;
+    int rc = HPF_OK;
+    auto cleanup = [&]() {
+        cudaFree(u32);
+        cudaFree(i32);
+        cudaFree(d_bad);
+        if (to_free) cudaFree(to_free);
+    };
+    const size_t n1 = (size_t)(nnz > 0 ? nnz : 1);
+    if (cudaMalloc(&u32, 4 * n1) != cudaSuccess || cudaMalloc(&i32, 4 * n1) != cudaSuccess ||
+        cudaMalloc(&d_bad, 4) != cudaSuccess) {
+        cleanup();
+        h->nnz = 0;
+        return fail(HPF_ENOMEM, "device allocation failed in hpf_load_coo");
+    }
+    cudaMemsetAsync(d_bad, 0, 4, h->stream);
+    rc = stage_index(h, ix_u, nnz, index_bytes, h->nU, u32, d_bad);
+    if (rc == HPF_OK) rc = stage_index(h, ix_i, nnz, index_bytes, h->nI, i32, d_bad);
+    if (rc == HPF_OK) rc = stage_in(h, Y, (size_t)nnz * h->rb, &yv, &to_free);
+    int bad = 0;
+    if (rc == HPF_OK && cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, h->stream) == cudaSuccess)
+        cudaStreamSynchronize(h->stream);
+    if (rc == HPF_OK && bad) rc = fail(HPF_EINVAL, "index out of range in ix_u/ix_i (nU=%lld, nI=%lld)", (long long)h->nU, (long long)h->nI);
+    if (rc == HPF_OK) {
+        if (h->rb == 4) {
+            rc = build_order<float>(h, u32, i32, (const float*)yv, nnz, h->nU, h->nI, &h->A_row, &h->A_col, &h->A_val);
+            if (rc == HPF_OK) rc = build_order<float>(h, i32, u32, (const float*)yv, nnz, h->nI, h->nU, &h->B_row, &h->B_col, &h->B_val);
+        } else {
+            rc = build_order<double>(h, u32, i32, (const double*)yv, nnz, h->nU, h->nI, &h->A_row, &h->A_col, &h->A_val);
+            if (rc == HPF_OK) rc = build_order<double>(h, i32, u32, (const double*)yv, nnz, h->nI, h->nU, &h->B_row, &h->B_col, &h->B_val);
+        }
+    }
+    cudaStreamSynchronize(h->stream);
+    cleanup();
+    if (rc != HPF_OK) {
+        std::string keep = g_err;
+        free_data(h);
+        g_err = keep;
+        return rc;
+    }
+    h->data_loaded = true;
+    return HPF_OK;
+}
+
+int hpf_sweep(hpf_engine* h) {
+    if (!h) return fail(HPF_EINVAL, "engine is NULL");
+    if (!h->data_loaded) return fail(HPF_ESTATE, "no data loaded (call hpf_load_coo first)");
+    DeviceGuard guard(h->device);
+    TRY(ensure_x(h));
+    return do_sweep(h);
+}
+
+int hpf_update_users(hpf_engine* h) {
+    if (!h) return fail(HPF_EINVAL, "engine is NULL");
+    if (!h->x_valid) return fail(HPF_ESTATE, "hpf_update_users must follow hpf_sweep");
+    DeviceGuard guard(h->device);
+    return do_update(h, true, true);
+}
+
+int hpf_update_items(hpf_engine* h) {
+    if (!h) return fail(HPF_EINVAL, "engine is NULL");
+    if (!h->x_valid) return fail(HPF_ESTATE, "hpf_update_items must follow hpf_sweep");
+    DeviceGuard guard(h->device);
+    // Tsum was produced by hpf_update_users (and all-reduced by the caller): do not zero it here
+    CK(cudaMemsetAsync(h->Bsum, 0, sizeof(double) * h->ld, h->stream));
+    TRY(dispatch(h->rb, h->ld, [&](auto cfg) {
+        using C = decltype(cfg);
+        return launch_update_rows<C>(h, false, true);
+    }));
+    h->mat_valid = true;
+    return HPF_OK;
+}
+
+int hpf_partials(hpf_engine* h, void** item_sums, int64_t* item_sums_count, void** theta_colsum, int64_t* theta_colsum_count) {
+    if (!h) return fail(HPF_EINVAL, "engine is NULL");
+    if (item_sums) *item_sums = h->accI;
+    if (item_sums_count) *item_sums_count = h->nI * h->ld;
+    if (theta_colsum) *theta_colsum = h->Tsum;
+    if (theta_colsum_count) *theta_colsum_count = h->k;
+    return HPF_OK;
+}
+
+int hpf_step_full(hpf_engine* h, int32_t niter) {
+    if (!h) return fail(HPF_EINVAL, "engine is NULL");
+    if (niter < 0) return fail(HPF_EINVAL, "niter must be >= 0");
+    if (!h->data_loaded) return fail(HPF_ESTATE, "no data loaded (call hpf_load_coo first)");
+    if (!h->state_loaded) return fail(HPF_ESTATE, "no state loaded (call hpf_load_state first)");
+    if (niter == 0) return HPF_OK;
+    DeviceGuard guard(h->device);
+    TRY(ensure_x(h));
+    h->mat_valid = false;
+    const bool graph = h->use_graph && !h->timing && h->stream != nullptr && h->stream != cudaStreamLegacy;
+    if (graph) {
+        if (!h->graph_lean) TRY(capture_iteration(h, false, &h->graph_lean));
+        if (!h->graph_mat) TRY(capture_iteration(h, true, &h->graph_mat));
+    }
+    for (int it = 0; it < niter; ++it) {
+        const bool mat = (it == niter - 1);  // only the last iteration of a call stores shp/rte
+        if (graph) {
+            CK(cudaGraphLaunch(mat ? h->graph_mat : h->graph_lean, h->stream));
+            h->launches += kLaunchesPerIteration;
+        } else {
+            TRY(one_iteration(h, mat));
+        }
+    }
+    h->mat_valid = true;
+    return HPF_OK;
+}
+
+int hpf_launch_count(hpf_engine* h, int64_t* out) {
+    if (!h || !out) return fail(HPF_EINVAL, "NULL argument");
+    *out = h->launches;
+    return HPF_OK;
+}
+
+int hpf_phase_ms(hpf_engine* h, double out[4], int64_t* iterations) {
+    if (!h || !out) return fail(HPF_EINVAL, "NULL argument");
+    for (int p = 0; p < 4; ++p) out[p] = h->phase_ms[p];
+    if (iterations) *iterations = h->phase_iters;
+    return HPF_OK;
+}
+
+int hpf_ld(hpf_engine* h, int32_t* out) {
+    if (!h || !out) return fail(HPF_EINVAL, "NULL argument");
+    *out = h->ld;
+    return HPF_OK;
+}
+
+// ---- scoring ---------------------------------------------------------------------------------------
+static int score_common(hpf_engine* h, const int* iu, const int* ii, const void* val, int64_t n, int full_llk,
+                        double* out4, void* pred) {
+    // E[x] matrices are materialised into the (otherwise idle between iterations) accumulators'
+    // sibling buffers: reuse xu/xi would destroy sweep state, so use scratch allocations
+    void *theta = nullptr, *beta = nullptr;
+    double* d_sums = nullptr;
+    int rc = HPF_OK;
+    cudaError_t e = cudaMalloc(&theta, h->mat_bytes(h->nU > 0 ? h->nU : 1));
+    if (e == cudaSuccess) e = cudaMalloc(&beta, h->mat_bytes(h->nI > 0 ? h->nI : 1));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_sums, sizeof(double) * (4 + 2 * (size_t)h->ld));
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_sums, 0, sizeof(double) * (4 + 2 * (size_t)h->ld), h->stream);
+    if (e != cudaSuccess) rc = fail(HPF_ENOMEM, "scratch allocation failed: %s", cudaGetErrorString(e));
+    if (rc == HPF_OK) {
+        rc = dispatch(h->rb, h->ld, [&](auto cfg) {
+            using C = decltype(cfg);
+            using real = typename C::real;
+            if (h->nU > 0) hpf::ratio_rows_kernel<real><<<nblk(h->nU * h->ld), 256, 0, h->stream>>>(h->nU, h->ld, h->k, (const real*)h->Gshp, (const real*)h->Grte, (real*)theta);
+            if (h->nI > 0) hpf::ratio_rows_kernel<real><<<nblk(h->nI * h->ld), 256, 0, h->stream>>>(h->nI, h->ld, h->k, (const real*)h->Lshp, (const real*)h->Lrte, (real*)beta);
+            h->launches += 2;
+            CKK();
+            if (n > 0) {
+                const int gpb = 256 / C::lpg;
+                long long want = (n + gpb - 1) / gpb;
+                if (want > 148 * 16) want = 148 * 16;
+                hpf::score_kernel<real, C::lpg, C::vpl><<<(unsigned)want, 256, 0, h->stream>>>(
+                    iu, ii, (const real*)val, n, (const real*)theta, (const real*)beta, h->ld, full_llk,
+                    out4 ? d_sums : nullptr, (real*)pred);
+                h->launches++;
+                CKK();
+            }
+            if (out4) {
+                const size_t smem = sizeof(double) * h->ld;
+                if (h->nU > 0) hpf::colsum_kernel<real><<<148 * 4, 256, smem, h->stream>>>(h->nU, h->ld, h->k, (const real*)theta, (const real*)nullptr, d_sums + 4);
+                if (h->nI > 0) hpf::colsum_kernel<real><<<148 * 4, 256, smem, h->stream>>>(h->nI, h->ld, h->k, (const real*)beta, (const real*)nullptr, d_sums + 4 + h->ld);
+                hpf::dot_cols_kernel<<<1, 32, 0, h->stream>>>(h->k, d_sums + 4, d_sums + 4 + h->ld, d_sums + 3);
+                h->launches += 3;
+                CKK();
+            }
+            return HPF_OK;
+        });
+    }
+    if (rc == HPF_OK && out4) {
+        e = cudaMemcpyAsync(out4, d_sums, sizeof(double) * 4, cudaMemcpyDeviceToHost, h->stream);
+        if (e != cudaSuccess) rc = fail(HPF_ECUDA, "D2H failed: %s", cudaGetErrorString(e));
+    }
+    e = cudaStreamSynchronize(h->stream);
+    if (rc == HPF_OK && e != cudaSuccess) rc = fail(HPF_ECUDA, "score kernels failed: %s", cudaGetErrorString(e));
+    cudaFree(theta);
+    cudaFree(beta);
+    cudaFree(d_sums);
+    return rc;
+}
+
+int hpf_llk_train(hpf_engine* h, int32_t full_llk, double out[4]) {
+    if (!h || !out) return fail(HPF_EINVAL, "NULL argument");
+    if (!h->data_loaded || !h->state_loaded || !h->mat_valid) return fail(HPF_ESTATE, "needs loaded data and state");
+    DeviceGuard guard(h->device);
+    return score_common(h, h->A_row, h->A_col, h->A_val, h->nnz, full_llk, out, nullptr);
+}
+
+static int score_external(hpf_engine* h, const void* ix_u, const void* ix_i, const void* Y, int64_t n,
+                          int32_t index_bytes, int full_llk, double* out4, void* pred_out) {
+    if (n < 0 || n >= (1ll << 31)) return fail(HPF_EINVAL, "n out of range");
+    if (index_bytes != 4 && index_bytes != 8) return fail(HPF_EINVAL, "index_bytes must be 4 or 8");
+    if (!h->state_loaded || !h->mat_valid) return fail(HPF_ESTATE, "no state loaded");
+    DeviceGuard guard(h->device);
+    int *u32 = nullptr, *i32 = nullptr, *d_bad = nullptr;
+    void *yfree = nullptr, *pred_dev = nullptr;
+    const void* yv = nullptr;
+    const size_t n1 = (size_t)(n > 0 ? n : 1);
+    int rc = HPF_OK;
+    if (cudaMalloc(&u32, 4 * n1) != cudaSuccess || cudaMalloc(&i32, 4 * n1) != cudaSuccess || cudaMalloc(&d_bad, 4) != cudaSuccess)
+        rc = fail(HPF_ENOMEM, "device allocation failed");
+    if (rc == HPF_OK) {
+        cudaMemsetAsync(d_bad, 0, 4, h->stream);
+        rc = stage_index(h, ix_u, n, index_bytes, h->nU, u32, d_bad);
+    }
+    if (rc == HPF_OK) rc = stage_index(h, ix_i, n, index_bytes, h->nI, i32, d_bad);
+    if (rc == HPF_OK && Y) rc = stage_in(h, Y, (size_t)n * h->rb, &yv, &yfree);
+    int bad = 0;
+    if (rc == HPF_OK) {
+        cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, h->stream);
+        cudaStreamSynchronize(h->stream);
+        if (bad) rc = fail(HPF_EINVAL, "index out of range");
+    }
+    const bool pred_is_dev = pred_out && is_device_ptr(pred_out);
+    if (rc == HPF_OK && pred_out && !pred_is_dev && cudaMalloc(&pred_dev, n1 * h->rb) != cudaSuccess)
+        rc = fail(HPF_ENOMEM, "device allocation failed");
+    if (rc == HPF_OK) rc = score_common(h, u32, i32, yv, n, full_llk, out4, pred_out ? (pred_is_dev ? pred_out : pred_dev) : nullptr);
+    if (rc == HPF_OK && pred_dev && n > 0) {
+        if (cudaMemcpy(pred_out, pred_dev, (size_t)n * h->rb, cudaMemcpyDeviceToHost) != cudaSuccess)
+            rc = fail(HPF_ECUDA, "D2H of predictions failed");
+    }
+    cudaFree(u32);
+    cudaFree(i32);
+    cudaFree(d_bad);
+    cudaFree(yfree);
+    cudaFree(pred_dev);
+    return rc;
+}
+
+int hpf_llk(hpf_engine* h, const void* ix_u, const void* ix_i, const void* Y, int64_t nnz, int32_t index_bytes,
+            int32_t full_llk, double out[4]) {
+    if (!h || !out || (nnz > 0 && (!ix_u || !ix_i || !Y))) return fail(HPF_EINVAL, "NULL argument");
+    return score_external(h, ix_u, ix_i, Y, nnz, index_bytes, full_llk, out, nullptr);
+}
+
+int hpf_predict(hpf_engine* h, const void* ix_u, const void* ix_i, int64_t n, int32_t index_bytes, void* out) {
+    if (!h || (n > 0 && (!ix_u || !ix_i || !out))) return fail(HPF_EINVAL, "NULL argument");
+    return score_external(h, ix_u, ix_i, nullptr, n, index_bytes, 0, nullptr, out);
+}
+
+// ---- stateless L1 forms -------------------------------------------------------------------------------
+int hpf_update_shapes(int32_t real_bytes, int32_t index_bytes, int32_t device, void* G_sh, const void* G_rt,
+                      void* L_sh, const void* L_rt, void* phi, const void* Y, const void* ix_u, const void* ix_i,
+                      int64_t nU, int64_t nI, int64_t nY, int32_t k, double a, double c) {
+    if (!G_sh || !G_rt || !L_sh || !L_rt) return fail(HPF_EINVAL, "NULL state array");
+    hpf_engine* h = nullptr;
+    TRY(hpf_create(&h, nU, nI, k, real_bytes, device));
+    DeviceGuard guard(device);
+    int rc = HPF_OK;
+    void *kr = nullptr, *tr = nullptr, *phi_dev = nullptr;
+    int *u32 = nullptr, *i32 = nullptr, *d_bad = nullptr;
+    void* yfree = nullptr;
+    const void* yv = nullptr;
+    const size_t n1 = (size_t)(nY > 0 ? nY : 1);
+    do {
+        // rate vectors are not touched by these two loops; upload dummies
+        std::vector<char> ones((size_t)(nU > nI ? nU : nI) * real_bytes + 8, 0);
+        if ((rc = hpf_load_state(h, G_sh, G_rt, L_sh, L_rt, ones.data(), ones.data())) != HPF_OK) break;
+        if ((rc = ensure_x(h)) != HPF_OK) break;
+        if (cudaMalloc(&u32, 4 * n1) != cudaSuccess || cudaMalloc(&i32, 4 * n1) != cudaSuccess || cudaMalloc(&d_bad, 4) != cudaSuccess) {
+            rc = fail(HPF_ENOMEM, "device allocation failed");
+            break;
+        }
+        cudaMemsetAsync(d_bad, 0, 4, h->stream);
+        if ((rc = stage_index(h, ix_u, nY, index_bytes, nU, u32, d_bad)) != HPF_OK) break;
+        if ((rc = stage_index(h, ix_i, nY, index_bytes, nI, i32, d_bad)) != HPF_OK) break;
+        if ((rc = stage_in(h, Y, (size_t)nY * real_bytes, &yv, &yfree)) != HPF_OK) break;
+        int bad = 0;
+        cudaMemcpy(&bad, d_bad, 4, cudaMemcpyDeviceToHost);
+        if (bad) {
+            rc = fail(HPF_EINVAL, "index out of range");
+            break;
+        }
+        const bool phi_dev_dst = phi && is_device_ptr(phi);
+        if (phi && !phi_dev_dst && cudaMalloc(&phi_dev, n1 * (size_t)k * real_bytes) != cudaSuccess) {
+            rc = fail(HPF_ENOMEM, "device allocation of phi failed");
+            break;
+        }
+        void* phi_target = phi ? (phi_dev_dst ? phi : phi_dev) : nullptr;
+        rc = dispatch(real_bytes, h->ld, [&](auto cfg) {
+            using C = decltype(cfg);
+            using real = typename C::real;
+            TRY(launch_sweep_coo<C>(h, u32, i32, yv, nY, h->xu, h->xi, h->accU, h->accI, h->ld, phi_target, k, h->stream));
+            if (nU > 0) hpf::finish_shapes_kernel<real><<<nblk(nU * h->ld), 256, 0, h->stream>>>(nU * h->ld, (const real*)h->xu, (const real*)h->accU, (real*)h->Gshp, (real)a);
+            if (nI > 0) hpf::finish_shapes_kernel<real><<<nblk(nI * h->ld), 256, 0, h->stream>>>(nI * h->ld, (const real*)h->xi, (const real*)h->accI, (real*)h->Lshp, (real)c);
+            CKK();
+            return HPF_OK;
+        });
+        if (rc != HPF_OK) break;
+        if ((rc = hpf_export_state(h, G_sh, nullptr, L_sh, nullptr, nullptr, nullptr, nullptr, nullptr)) != HPF_OK) break;
+        if (phi_dev && nY > 0 && cudaMemcpy(phi, phi_dev, (size_t)nY * k * real_bytes, cudaMemcpyDeviceToHost) != cudaSuccess)
+            rc = fail(HPF_ECUDA, "D2H of phi failed");
+    } while (0);
+    std::string keep = g_err;
+    cudaFree(kr);
+    cudaFree(tr);
+    cudaFree(phi_dev);
+    cudaFree(u32);
+    cudaFree(i32);
+    cudaFree(d_bad);
+    cudaFree(yfree);
+    hpf_destroy(h);
+    g_err = keep;
+    return rc;
+}
+
+int hpf_digamma(int32_t real_bytes, int32_t device, const void* x, void* out, int64_t n) {
+    if (real_bytes != 4 && real_bytes != 8) return fail(HPF_EINVAL, "real_bytes must be 4 or 8");
+    if (n < 0 || (n > 0 && (!x || !out))) return fail(HPF_EINVAL, "bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return fail(HPF_ECUDA, "no such CUDA device %d", device);
+    }
+    if (n == 0) return HPF_OK;
+    DeviceGuard guard(device);
+    void *dx = nullptr, *dout = nullptr;
+    const size_t bytes = (size_t)n * real_bytes;
+    int rc = HPF_OK;
+    if (cudaMalloc(&dx, bytes) != cudaSuccess || cudaMalloc(&dout, bytes) != cudaSuccess) rc = fail(HPF_ENOMEM, "device allocation failed");
+    if (rc == HPF_OK && cudaMemcpy(dx, x, bytes, cudaMemcpyDefault) != cudaSuccess) rc = fail(HPF_ECUDA, "copy in failed");
+    if (rc == HPF_OK) {
+        if (real_bytes == 4)
+            hpf::digamma_kernel<float><<<nblk(n), 256>>>((const float*)dx, (float*)dout, n);
+        else
+            hpf::digamma_kernel<double><<<nblk(n), 256>>>((const double*)dx, (double*)dout, n);
+        if (cudaGetLastError() != cudaSuccess || cudaMemcpy(out, dout, bytes, cudaMemcpyDefault) != cudaSuccess)
+            rc = fail(HPF_ECUDA, "digamma kernel failed");
+    }
+    cudaFree(dx);
+    cudaFree(dout);
+    return rc;
+}
+
+}  // extern "C"
+
+#include "hpf_batch_host.inl"

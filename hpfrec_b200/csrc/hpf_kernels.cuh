@@ -1,0 +1,504 @@
+// Kernels of the HPF coordinate-ascent engine (sm_100a).  See DESIGN.md for the data layout and the
+// roofline of each kernel.  Reference = david-cortes/hpfrec, hpfrec/cython_loops.pxi ("pxi").
+//
+// Key identity used throughout: the reference's multinomial parameter (update_phi, pxi:551-577)
+//     phi[n,j] = Y[n] * softmax_j( Eu[u,j] + Ei[i,j] ),   Eu = psi(G_sh) - log(G_rt),  Ei likewise
+// factorises into per-ROW quantities:  with  xu[u,j] = exp(Eu[u,j] - max_j Eu[u,:])  and xi likewise,
+//     phi[n,j] = Y[n] * xu[u,j]*xi[i,j] / dot(xu[u,:], xi[i,:]).
+// So psi/log/exp are evaluated once per factor ROW per iteration ((nU+nI)*k times) instead of once
+// per nnz (nnz*k times), phi is never materialised, and the scatter (update_G_n_L_sh, pxi:613-621)
+// becomes  G_sh[u,:] = a + xu[u,:] * sum_{n in u} w_n xi[i_n,:],   w_n = Y[n]/dot  (mirror for L_sh).
+#pragma once
+#include "hpf_device.cuh"
+
+namespace hpf {
+
+// =============================================================================================
+// K2  cavi sweep, one direction ("major" side = rows owned by consecutive nnz, "minor" = gathered)
+//     replaces update_phi (pxi:551) + update_G_n_L_sh (pxi:613) for ONE of the two shape matrices.
+//     nnz are sorted by (L2 panel of the minor id, major id); every lane group walks a contiguous
+//     chunk, keeps the major row's x and the running sum in registers, gathers the minor row with
+//     128-bit loads, reduces the normaliser with shuffles inside the group, and flushes the running
+//     sum with one vector RED per pack when the major id changes (so atomics happen once per
+//     (row, chunk) segment, not once per nnz).
+//       acc[r, :] += sum_{n in segment} (Y[n] / dot(xown[r], xgat[c_n])) * xgat[c_n, :]
+// =============================================================================================
+template <typename real, int LPG, int VPL, int UNROLL>
+__global__ void __launch_bounds__(256)
+sweep_major_kernel(const int* __restrict__ row, const int* __restrict__ col,
+                   const real* __restrict__ val, long long nnz, int chunk,
+                   const real* __restrict__ xown, const real* __restrict__ xgat,
+                   real* __restrict__ acc, int ld) {
+    constexpr int EPV = Pack<real>::N;
+    static_assert(LPG % UNROLL == 0, "UNROLL must divide LPG");
+    const int gl = (threadIdx.x & 31) % LPG;
+    const long long group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPG;
+    const long long beg = group * (long long)chunk;
+    if (beg >= nnz) return;  // whole groups leave together; shuffles below use the group mask
+    const long long end = (beg + chunk < nnz) ? beg + chunk : nnz;
+    const unsigned gmask = group_mask<LPG>();
+
+    int off[VPL];
+    bool act[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        off[v] = (gl + LPG * v) * EPV;
+        act[v] = off[v] < ld;
+    }
+    Pack<real> own[VPL], sum[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        own[v] = pack_zero<real>();
+        sum[v] = pack_zero<real>();
+    }
+    int cur = -1;
+
+    for (long long base = beg; base < end; base += LPG) {
+        // coalesced fetch of LPG triples (one per lane), broadcast inside the group below
+        const long long idx = base + gl;
+        int r = -1, c = 0;
+        real y = real(0);
+        if (idx < end) {
+            r = __ldg(row + idx);
+            c = __ldg(col + idx);
+            y = __ldg(val + idx);
+        }
+#pragma unroll
+        for (int t0 = 0; t0 < LPG; t0 += UNROLL) {
+            if (base + t0 >= end) break;  // uniform inside the group
+            Pack<real> g[UNROLL][VPL];
+            int rr[UNROLL];
+            real yy[UNROLL];
+#pragma unroll
+            for (int q = 0; q < UNROLL; ++q) {
+                const int cc = __shfl_sync(gmask, c, t0 + q, LPG);
+                rr[q] = __shfl_sync(gmask, r, t0 + q, LPG);
+                yy[q] = __shfl_sync(gmask, y, t0 + q, LPG);
+                const real* src = xgat + (size_t)cc * ld;
+#pragma unroll
+                for (int v = 0; v < VPL; ++v)
+                    g[q][v] = act[v] ? ldg_pack(src + off[v]) : pack_zero<real>();
+            }
+#pragma unroll
+            for (int q = 0; q < UNROLL; ++q) {
+                if (rr[q] < 0) continue;  // past the end of the chunk (uniform inside the group)
+                if (rr[q] != cur) {
+                    if (cur >= 0) {
+#pragma unroll
+                        for (int v = 0; v < VPL; ++v)
+                            if (act[v]) red_add_pack(acc + (size_t)cur * ld + off[v], sum[v]);
+                    }
+                    cur = rr[q];
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) {
+                        own[v] = act[v] ? ldg_pack(xown + (size_t)cur * ld + off[v]) : pack_zero<real>();
+                        sum[v] = pack_zero<real>();
+                    }
+                }
+                real s = real(0);
+#pragma unroll
+                for (int v = 0; v < VPL; ++v)
+#pragma unroll
+                    for (int e = 0; e < EPV; ++e) s = fma(own[v].v[e], g[q][v].v[e], s);
+                s = group_sum<LPG>(s, gmask);
+                const real w = rdiv_fast(yy[q], s);
+#pragma unroll
+                for (int v = 0; v < VPL; ++v)
+#pragma unroll
+                    for (int e = 0; e < EPV; ++e) sum[v].v[e] = fma(w, g[q][v].v[e], sum[v].v[e]);
+            }
+        }
+    }
+    if (cur >= 0) {
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+            if (act[v]) red_add_pack(acc + (size_t)cur * ld + off[v], sum[v]);
+    }
+}
+
+// =============================================================================================
+// K2'  single-pass COO sweep with atomics on both sides: any nnz order, used for minibatches
+//      (partial_fit pxi:438-459, SVI pxi:292-314) and as the cross-check of the two-pass sweep.
+//      accU[u,:] += w_n * xi[i,:]    accI[i,:] += w_n * xu[u,:]     (optionally phi[n,:] written)
+// =============================================================================================
+template <typename real, int LPG, int VPL>
+__global__ void __launch_bounds__(256)
+sweep_coo_kernel(const int* __restrict__ iu, const int* __restrict__ ii, const real* __restrict__ val,
+                 long long nnz, int chunk, const real* __restrict__ xu, const real* __restrict__ xi,
+                 real* __restrict__ accU, real* __restrict__ accI, int ld,
+                 real* __restrict__ phi, int k) {
+    constexpr int EPV = Pack<real>::N;
+    const int gl = (threadIdx.x & 31) % LPG;
+    const long long group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPG;
+    const long long beg = group * (long long)chunk;
+    if (beg >= nnz) return;
+    const long long end = (beg + chunk < nnz) ? beg + chunk : nnz;
+    const unsigned gmask = group_mask<LPG>();
+    int off[VPL];
+    bool act[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        off[v] = (gl + LPG * v) * EPV;
+        act[v] = off[v] < ld;
+    }
+    for (long long base = beg; base < end; base += LPG) {
+        const long long idx = base + gl;
+        int u = 0, i = 0;
+        real y = real(0);
+        if (idx < end) {
+            u = __ldg(iu + idx);
+            i = __ldg(ii + idx);
+            y = __ldg(val + idx);
+        }
+        const int cnt = (end - base < LPG) ? (int)(end - base) : LPG;
+        for (int t = 0; t < cnt; ++t) {
+            const int uu = __shfl_sync(gmask, u, t, LPG);
+            const int it = __shfl_sync(gmask, i, t, LPG);
+            const real yy = __shfl_sync(gmask, y, t, LPG);
+            Pack<real> gu[VPL], gi[VPL];
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                gu[v] = act[v] ? ldg_pack(xu + (size_t)uu * ld + off[v]) : pack_zero<real>();
+                gi[v] = act[v] ? ldg_pack(xi + (size_t)it * ld + off[v]) : pack_zero<real>();
+            }
+            real s = real(0);
+#pragma unroll
+            for (int v = 0; v < VPL; ++v)
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) s = fma(gu[v].v[e], gi[v].v[e], s);
+            s = group_sum<LPG>(s, gmask);
+            const real w = rdiv_fast(yy, s);
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                if (!act[v]) continue;
+                Pack<real> pu, pi;
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) {
+                    pu.v[e] = w * gi[v].v[e];
+                    pi.v[e] = w * gu[v].v[e];
+                }
+                red_add_pack(accU + (size_t)uu * ld + off[v], pu);
+                red_add_pack(accI + (size_t)it * ld + off[v], pi);
+                if (phi != nullptr) {
+#pragma unroll
+                    for (int e = 0; e < EPV; ++e)
+                        if (off[v] + e < k)
+                            phi[(size_t)(base + t) * k + off[v] + e] = pu.v[e] * gu[v].v[e];
+                }
+            }
+        }
+    }
+}
+
+// =============================================================================================
+// K1+K3 fused row update for full-batch CAVI (one lane group per factor row):
+//   shp  = prior + x * acc                       pxi:239-249 (scatter result) ; acc is re-zeroed
+//   rte  = shp_rate / rate[r] + colsum_other[j]  pxi:236 (users) / pxi:255 (items)
+//   E[x] = shp / rte                             pxi:251 / 256  -> column sums (double) for the other side
+//   rate[r] = add_rate + sum_j E[x]              pxi:258 / 259
+//   x    = exp(psi(shp) - log(rte) - rowmax)     the per-row factor of next iteration's update_phi
+// MAT=true also stores shp and rte (needed for export / minibatch steps); lean iterations skip that.
+// =============================================================================================
+template <typename real, int LPG, int VPL, bool MAT>
+__global__ void __launch_bounds__(256)
+update_rows_kernel(int nrows, int ld, int k, real* __restrict__ x, real* __restrict__ acc,
+                   real* __restrict__ shp_out, real* __restrict__ rte_out, real* __restrict__ rate,
+                   const double* __restrict__ colsum_other, double* __restrict__ colsum_out,
+                   real prior, real shp_rate, real add_rate) {
+    constexpr int EPV = Pack<real>::N;
+    extern __shared__ double s_col[];  // ld doubles
+    for (int j = threadIdx.x; j < ld; j += blockDim.x) s_col[j] = 0.0;
+    __syncthreads();
+
+    const int gl = (threadIdx.x & 31) % LPG;
+    const unsigned gmask = group_mask<LPG>();
+    const int groups_per_block = blockDim.x / LPG;
+    const int g0 = blockIdx.x * groups_per_block + threadIdx.x / LPG;
+    const int gstride = gridDim.x * groups_per_block;
+
+    int off[VPL];
+    bool act[VPL];
+    real other[VPL][EPV];
+    real csum[VPL][EPV];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        off[v] = (gl + LPG * v) * EPV;
+        act[v] = off[v] < ld;
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) {
+            const int j = off[v] + e;
+            other[v][e] = (act[v] && j < k) ? (real)colsum_other[j] : real(0);
+            csum[v][e] = real(0);
+        }
+    }
+
+    for (int r = g0; r < nrows; r += gstride) {
+        const real inv = shp_rate / rate[r];
+        Pack<real> shp[VPL], rte[VPL], E[VPL];
+        real rowsum = real(0);
+        real m = -INFINITY;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            if (!act[v]) continue;
+            const Pack<real> xv = ld_pack(x + (size_t)r * ld + off[v]);
+            const Pack<real> av = ld_pack(acc + (size_t)r * ld + off[v]);
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) {
+                const bool real_col = off[v] + e < k;
+                const real s_ = fma(xv.v[e], av.v[e], prior);
+                const real t_ = inv + other[v][e];
+                shp[v].v[e] = real_col ? s_ : real(0);
+                rte[v].v[e] = real_col ? t_ : real(1);
+                const real th = real_col ? s_ / t_ : real(0);
+                rowsum += th;
+                csum[v][e] += th;
+                const real lg = real_col ? digamma(s_) - rlog(t_) : -INFINITY;
+                E[v].v[e] = lg;
+                m = lg > m ? lg : m;
+            }
+        }
+        rowsum = group_sum<LPG>(rowsum, gmask);
+        m = group_max<LPG>(m, gmask);
+        if (gl == 0) rate[r] = add_rate + rowsum;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            if (!act[v]) continue;
+            Pack<real> xn;
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) xn.v[e] = (off[v] + e < k) ? rexp(E[v].v[e] - m) : real(0);
+            st_pack(x + (size_t)r * ld + off[v], xn);
+            st_pack(acc + (size_t)r * ld + off[v], pack_zero<real>());
+            if (MAT) {
+                st_pack(shp_out + (size_t)r * ld + off[v], shp[v]);
+                st_pack(rte_out + (size_t)r * ld + off[v], rte[v]);
+            }
+        }
+    }
+    // column sums: registers -> shared (double) -> one global atomic per column per block
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        if (!act[v]) continue;
+#pragma unroll
+        for (int e = 0; e < EPV; ++e)
+            if (off[v] + e < k) atomicAdd(&s_col[off[v] + e], (double)csum[v][e]);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < k; j += blockDim.x) atomicAdd(colsum_out + j, s_col[j]);
+}
+
+// =============================================================================================
+// K1 alone: x rows from materialised (shp, rte); optional row list (minibatch) and optional column
+// sums of shp/rte (used to seed Beta.sum(axis=0) after a state upload).
+// =============================================================================================
+template <typename real, int LPG, int VPL>
+__global__ void __launch_bounds__(256)
+rows_to_x_kernel(int nrows, const int* __restrict__ rows, int ld, int k, const real* __restrict__ shp,
+                 const real* __restrict__ rte, real* __restrict__ x, double* __restrict__ colsum_out) {
+    constexpr int EPV = Pack<real>::N;
+    extern __shared__ double s_col[];
+    if (colsum_out != nullptr) {
+        for (int j = threadIdx.x; j < ld; j += blockDim.x) s_col[j] = 0.0;
+        __syncthreads();
+    }
+    const int gl = (threadIdx.x & 31) % LPG;
+    const unsigned gmask = group_mask<LPG>();
+    const int groups_per_block = blockDim.x / LPG;
+    const int g0 = blockIdx.x * groups_per_block + threadIdx.x / LPG;
+    const int gstride = gridDim.x * groups_per_block;
+    int off[VPL];
+    bool act[VPL];
+    real csum[VPL][EPV];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        off[v] = (gl + LPG * v) * EPV;
+        act[v] = off[v] < ld;
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) csum[v][e] = real(0);
+    }
+    for (int q = g0; q < nrows; q += gstride) {
+        const int r = rows ? rows[q] : q;
+        Pack<real> E[VPL];
+        real m = -INFINITY;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            if (!act[v]) continue;
+            const Pack<real> sv = ld_pack(shp + (size_t)r * ld + off[v]);
+            const Pack<real> tv = ld_pack(rte + (size_t)r * ld + off[v]);
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) {
+                const bool real_col = off[v] + e < k;
+                const real lg = real_col ? digamma(sv.v[e]) - rlog(tv.v[e]) : -INFINITY;
+                E[v].v[e] = lg;
+                m = lg > m ? lg : m;
+                if (real_col) csum[v][e] += sv.v[e] / tv.v[e];
+            }
+        }
+        m = group_max<LPG>(m, gmask);
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            if (!act[v]) continue;
+            Pack<real> xn;
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) xn.v[e] = (off[v] + e < k) ? rexp(E[v].v[e] - m) : real(0);
+            st_pack(x + (size_t)r * ld + off[v], xn);
+        }
+    }
+    if (colsum_out != nullptr) {
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            if (!act[v]) continue;
+#pragma unroll
+            for (int e = 0; e < EPV; ++e)
+                if (off[v] + e < k) atomicAdd(&s_col[off[v] + e], (double)csum[v][e]);
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < k; j += blockDim.x) atomicAdd(colsum_out + j, s_col[j]);
+    }
+}
+
+// shp = prior + x * acc for every row (finishes a stand-alone hpf_update_shapes call)
+template <typename real>
+__global__ void finish_shapes_kernel(long long n_elems, const real* __restrict__ x,
+                                     const real* __restrict__ acc, real* __restrict__ shp, real prior) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_elems) shp[i] = fma(x[i], acc[i], prior);
+}
+
+// =============================================================================================
+// ingest helpers
+// =============================================================================================
+template <typename IDX>
+__global__ void convert_index_kernel(const IDX* __restrict__ in, int* __restrict__ out, long long n,
+                                     long long limit, int* __restrict__ bad) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long v = (long long)in[i];
+    if (v < 0 || v >= limit) atomicExch(bad, 1);
+    out[i] = (int)v;
+}
+
+// sort key of one ordering: (panel of the minor id, major id)
+__global__ void make_keys_kernel(const int* __restrict__ major, const int* __restrict__ minor,
+                                 long long n, int minor_per_panel, unsigned long long major_span,
+                                 unsigned long long* __restrict__ keys, unsigned* __restrict__ perm) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long panel = (unsigned long long)(minor[i] / minor_per_panel);
+    keys[i] = panel * major_span + (unsigned long long)major[i];
+    perm[i] = (unsigned)i;
+}
+
+template <typename real>
+__global__ void apply_order_kernel(const unsigned long long* __restrict__ keys_sorted,
+                                   const unsigned* __restrict__ perm, long long n,
+                                   unsigned long long major_span, const int* __restrict__ minor,
+                                   const real* __restrict__ val, int* __restrict__ out_row,
+                                   int* __restrict__ out_col, real* __restrict__ out_val) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned p = perm[i];
+    out_row[i] = (int)(keys_sorted[i] % major_span);
+    out_col[i] = minor[p];
+    out_val[i] = val[p];
+}
+
+// strided copy helpers between packed (n x k) caller layout and padded (n x ld) engine layout
+template <typename real>
+__global__ void pad_rows_kernel(const real* __restrict__ in, real* __restrict__ out, long long nrows,
+                                int k, int ld, real fill) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows * ld) return;
+    const long long r = i / ld;
+    const int j = (int)(i - r * ld);
+    out[i] = j < k ? in[r * k + j] : fill;
+}
+template <typename real>
+__global__ void unpad_rows_kernel(const real* __restrict__ in, const real* __restrict__ denom,
+                                  real* __restrict__ out, long long nrows, int k, int ld) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows * k) return;
+    const long long r = i / k;
+    const int j = (int)(i - r * k);
+    const real v = in[r * ld + j];
+    out[i] = denom ? v / denom[r * ld + j] : v;
+}
+
+// =============================================================================================
+// K6/K7  llk_plus_rmse (pxi:627-658) + sum_prediction (pxi:816-825) + predict_multiple (pxi:803-810)
+//   yhat = sum_j (G_sh/G_rt)[u,j] * (L_sh/L_rt)[i,j]   evaluated from the materialised state
+//   out[0] += Y log yhat [- lgamma(Y+1)],  out[1] += (Y-yhat)^2,  out[2] += yhat   (double sums)
+// =============================================================================================
+template <typename real, int LPG, int VPL>
+__global__ void __launch_bounds__(256)
+score_kernel(const int* __restrict__ iu, const int* __restrict__ ii, const real* __restrict__ val,
+             long long n, const real* __restrict__ theta, const real* __restrict__ beta, int ld,
+             int full_llk, double* __restrict__ sums, real* __restrict__ pred) {
+    constexpr int EPV = Pack<real>::N;
+    __shared__ double s_part[3];
+    if (threadIdx.x < 3) s_part[threadIdx.x] = 0.0;
+    __syncthreads();
+    const int gl = (threadIdx.x & 31) % LPG;
+    const unsigned gmask = group_mask<LPG>();
+    const int groups_per_block = blockDim.x / LPG;
+    const long long g0 = (long long)blockIdx.x * groups_per_block + threadIdx.x / LPG;
+    const long long gstride = (long long)gridDim.x * groups_per_block;
+    int off[VPL];
+    bool act[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        off[v] = (gl + LPG * v) * EPV;
+        act[v] = off[v] < ld;
+    }
+    double l0 = 0.0, l1 = 0.0, l2 = 0.0;
+    // every group of the warp runs the same number of trips (shuffles need converged groups only,
+    // but keeping warps converged is cheaper); out-of-range trips are masked
+    const long long trips = (n + gstride - 1) / gstride;
+    for (long long t = 0; t < trips; ++t) {
+        const long long q = g0 + t * gstride;
+        const bool live = q < n;
+        const int u = live ? iu[q] : 0;
+        const int i = live ? ii[q] : 0;
+        real s = real(0);
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            if (!act[v]) continue;
+            const Pack<real> a = ldg_pack(theta + (size_t)u * ld + off[v]);
+            const Pack<real> b = ldg_pack(beta + (size_t)i * ld + off[v]);
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) s = fma(a.v[e], b.v[e], s);
+        }
+        s = group_sum<LPG>(s, gmask);
+        if (live && gl == 0) {
+            if (pred != nullptr) pred[q] = s;
+            if (sums != nullptr) {
+                const double y = (double)val[q];
+                const double yh = (double)s;
+                l0 += full_llk ? y * log(yh) - lgamma(y + 1.0) : (double)((real)y * rlog(s));
+                const real d = (real)y - s;
+                l1 += (double)(d * d);
+                l2 += yh;
+            }
+        }
+    }
+    if (sums != nullptr) {
+        if (gl == 0) {
+            atomicAdd(&s_part[0], l0);
+            atomicAdd(&s_part[1], l1);
+            atomicAdd(&s_part[2], l2);
+        }
+        __syncthreads();
+        if (threadIdx.x < 3) atomicAdd(sums + threadIdx.x, s_part[threadIdx.x]);
+    }
+}
+
+// materialise E[x] = shp / rte (padded layout, pad columns -> 0) and its column sums
+template <typename real>
+__global__ void ratio_rows_kernel(long long nrows, int ld, int k, const real* __restrict__ shp,
+                                  const real* __restrict__ rte, real* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows * ld) return;
+    const int j = (int)(i % ld);
+    out[i] = j < k ? shp[i] / rte[i] : real(0);
+}
+
+}  // namespace hpf

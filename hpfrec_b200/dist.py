@@ -1,0 +1,82 @@
+"""User-sharded multi-GPU full-batch CAVI: one process per GPU, contiguous user ranges
+balanced by nnz, a full replica of the item side on every rank, and ONE exchange per iteration: the
+all-reduce (SUM) of the item-side partial sums (nI x ld reals) and of the k Theta column sums.
+torch.distributed (NCCL over NVLink/NVSwitch) is the plumbing; all compute is the engine's kernels.
+
+The prior `c` is added once, after the reduction (inside hpf_update_items), never per rank; every rank
+then recomputes the identical item update from identical reduced data, so replicas stay bit-identical
+without a broadcast.
+"""
+import numpy as np
+
+
+def plan_user_shards(ix_u, nU, world):
+    """Cut points (world+1 user ids, first 0, last nU) of contiguous user ranges holding ~equal nnz.
+    `ix_u` may be a numpy array or a torch tensor (any device)."""
+    if not isinstance(ix_u, np.ndarray) and hasattr(ix_u, "data_ptr"):   # torch tensor
+        import torch
+        deg = torch.bincount(ix_u.to(torch.int64), minlength=nU)
+        csum = torch.cumsum(deg, 0)
+        total = int(csum[-1].item()) if nU > 0 else 0
+        targets = torch.tensor([total * r / world for r in range(1, world)], device=csum.device,
+                               dtype=torch.float64)
+        inner = (torch.searchsorted(csum.to(torch.float64), targets) + 1).clamp(max=nU).tolist() if world > 1 else []
+    else:
+        deg = np.bincount(np.asarray(ix_u, dtype=np.int64), minlength=nU)
+        csum = np.cumsum(deg)
+        total = int(csum[-1]) if nU > 0 else 0
+        inner = [min(nU, int(np.searchsorted(csum, total * r / world) + 1)) for r in range(1, world)]
+    cuts = [0] + [int(c) for c in inner] + [nU]
+    for j in range(1, len(cuts)):            # monotone even for degenerate inputs
+        cuts[j] = max(cuts[j], cuts[j - 1])
+    return cuts
+
+
+def shard_triples(ix_u, ix_i, Y, lo, hi):
+    """Triples of users in [lo, hi) with user ids made local (numpy or torch, same type out)."""
+    sel = (ix_u >= lo) & (ix_u < hi)
+    return ix_u[sel] - lo, ix_i[sel], Y[sel]
+
+
+class _RawCuda:
+    def __init__(self, ptr, count, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr,
+                                         "data": (int(ptr), False), "version": 2}
+
+
+def wrap_device_buffer(ptr, count, torch_dtype, device=None):
+    """Zero-copy torch view of engine-owned device memory (for torch.distributed collectives)."""
+    import torch
+    typestr = {torch.float32: "<f4", torch.float64: "<f8"}[torch_dtype]
+    dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+    return torch.as_tensor(_RawCuda(ptr, count, typestr), device=dev)
+
+
+def engine_partial_tensors(engine, device=None):
+    """(item_sums, theta_colsum) torch views of an Engine's reduction buffers."""
+    import torch
+    p1, n1, p2, n2 = engine.partials()
+    real = torch.float32 if engine.real_bytes == 4 else torch.float64
+    return wrap_device_buffer(p1, n1, real, device), wrap_device_buffer(p2, n2, torch.float64, device)
+
+
+def run_sharded_iterations(engine, niter, partial_tensors=None, group=None, all_reduce=None):
+    """`niter` full-batch iterations of one user shard.  `engine` is an hpfrec_b200.engine.Engine (or
+    anything with sweep/update_users/update_items); the two tensors are all-reduced between the user
+    and the item update.  With world size 1 (or no process group) this equals Engine.step_full."""
+    import torch.distributed as dist
+    if all_reduce is None:
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            def all_reduce(t):
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        else:
+            def all_reduce(t):
+                return None
+    if partial_tensors is None:
+        partial_tensors = engine_partial_tensors(engine)
+    for _ in range(int(niter)):
+        engine.sweep()
+        engine.update_users()
+        for t in partial_tensors:
+            all_reduce(t)
+        engine.update_items()

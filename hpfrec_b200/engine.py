@@ -1,0 +1,221 @@
+"""Thin object wrapper over the C ABI (include/hpf_b200.h).  Arrays may be C-contiguous numpy arrays
+(host) or torch CUDA tensors (device); only their raw pointers cross into the library."""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+REAL_DTYPES = {4: np.float32, 8: np.float64}
+
+
+def _ptr(x, dtype=None, name="array"):
+    """Raw pointer of a numpy array / torch tensor; None -> NULL.  Keeps no reference."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        if not x.flags["C_CONTIGUOUS"]:
+            raise ValueError("%s must be C-contiguous" % name)
+        if dtype is not None and x.dtype != np.dtype(dtype):
+            raise ValueError("%s must have dtype %s, got %s" % (name, np.dtype(dtype), x.dtype))
+        return ctypes.c_void_p(x.ctypes.data)
+    if hasattr(x, "data_ptr"):  # torch tensor
+        if not x.is_contiguous():
+            raise ValueError("%s must be contiguous" % name)
+        if dtype is not None:
+            import torch
+            want = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
+                    np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64}[np.dtype(dtype)]
+            if x.dtype != want:
+                raise ValueError("%s must have dtype %s, got %s" % (name, want, x.dtype))
+        return ctypes.c_void_p(x.data_ptr())
+    raise TypeError("%s: expected numpy array or torch tensor" % name)
+
+
+def _index_bytes(x):
+    if isinstance(x, np.ndarray):
+        sz = x.dtype.itemsize
+        if x.dtype.kind not in "iu" or sz not in (4, 8):
+            raise ValueError("index arrays must be 32- or 64-bit integers, got %s" % x.dtype)
+        return sz
+    return x.element_size()
+
+
+def as_index(x):
+    """Host index array -> contiguous int32/int64/uint64 numpy array the C ABI accepts as-is."""
+    x = np.asarray(x)
+    if x.dtype.kind not in "iu" or x.dtype.itemsize not in (4, 8):
+        x = x.astype(np.int64)
+    return np.ascontiguousarray(x).reshape(-1)
+
+
+class Engine:
+    """One device-resident HPF state (+ optionally the training triples)."""
+
+    def __init__(self, nU, nI, k, real_bytes=4, device=0, stream=None):
+        self._lib = _lib.load()
+        self._h = ctypes.c_void_p()
+        self.nU, self.nI, self.k, self.real_bytes = int(nU), int(nI), int(k), int(real_bytes)
+        self.dtype = np.dtype(REAL_DTYPES[self.real_bytes])
+        _lib.check(self._lib.hpf_create(ctypes.byref(self._h), self.nU, self.nI, self.k, self.real_bytes,
+                                        int(device)))
+        if stream is not None:
+            self.set_stream(stream)
+
+    # -- life cycle ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.hpf_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- configuration --------------------------------------------------------------------------
+    def set_hyper(self, a, a_prime, b_prime, c, c_prime, d_prime):
+        _lib.check(self._lib.hpf_set_hyper(self._h, a, a_prime, b_prime, c, c_prime, d_prime))
+
+    def set_constants(self, a, c, k_shp, t_shp, add_k_rte, add_t_rte):
+        _lib.check(self._lib.hpf_set_constants(self._h, a, c, k_shp, t_shp, add_k_rte, add_t_rte))
+
+    def set_stream(self, stream):
+        """`stream`: an int/ctypes pointer (cudaStream_t) or a torch.cuda.Stream."""
+        ptr = getattr(stream, "cuda_stream", stream)
+        _lib.check(self._lib.hpf_set_stream(self._h, ctypes.c_void_p(int(ptr) if ptr else 0)))
+
+    def set_option(self, name, value):
+        _lib.check(self._lib.hpf_set_option(self._h, name.encode(), float(value)))
+
+    @property
+    def ld(self):
+        out = ctypes.c_int32()
+        _lib.check(self._lib.hpf_ld(self._h, ctypes.byref(out)))
+        return out.value
+
+    @property
+    def launch_count(self):
+        out = ctypes.c_int64()
+        _lib.check(self._lib.hpf_launch_count(self._h, ctypes.byref(out)))
+        return out.value
+
+    def phase_ms(self):
+        """(ms[4], iterations) accumulated since set_option('timing', 1): item-major pass, user-major
+        pass, user update, item update."""
+        out = (ctypes.c_double * 4)()
+        n = ctypes.c_int64()
+        _lib.check(self._lib.hpf_phase_ms(self._h, out, ctypes.byref(n)))
+        return list(out), n.value
+
+    # -- state ------------------------------------------------------------------------------------
+    def load_state(self, Gamma_shp, Gamma_rte, Lambda_shp, Lambda_rte, k_rte, t_rte):
+        dt = self.dtype
+        args = [_ptr(x, dt, n) for x, n in ((Gamma_shp, "Gamma_shp"), (Gamma_rte, "Gamma_rte"),
+                                            (Lambda_shp, "Lambda_shp"), (Lambda_rte, "Lambda_rte"),
+                                            (k_rte, "k_rte"), (t_rte, "t_rte"))]
+        _lib.check(self._lib.hpf_load_state(self._h, *args))
+
+    def export_state(self, Gamma_shp=None, Gamma_rte=None, Lambda_shp=None, Lambda_rte=None,
+                     k_rte=None, t_rte=None, Theta=None, Beta=None):
+        dt = self.dtype
+        args = [_ptr(x, dt) for x in (Gamma_shp, Gamma_rte, Lambda_shp, Lambda_rte, k_rte, t_rte, Theta, Beta)]
+        _lib.check(self._lib.hpf_export_state(self._h, *args))
+
+    def export_all(self):
+        """Convenience: fresh numpy arrays for the six state arrays + Theta, Beta."""
+        dt, k = self.dtype, self.k
+        out = dict(Gamma_shp=np.empty((self.nU, k), dt), Gamma_rte=np.empty((self.nU, k), dt),
+                   Lambda_shp=np.empty((self.nI, k), dt), Lambda_rte=np.empty((self.nI, k), dt),
+                   k_rte=np.empty((self.nU, 1), dt), t_rte=np.empty((self.nI, 1), dt),
+                   Theta=np.empty((self.nU, k), dt), Beta=np.empty((self.nI, k), dt))
+        self.export_state(**out)
+        return out
+
+    # -- data -------------------------------------------------------------------------------------
+    def load_coo(self, ix_u, ix_i, Y):
+        ib = _index_bytes(ix_u)
+        if _index_bytes(ix_i) != ib:
+            raise ValueError("ix_u and ix_i must have the same integer width")
+        n = int(Y.shape[0])
+        _lib.check(self._lib.hpf_load_coo(self._h, _ptr(ix_u, name="ix_u"), _ptr(ix_i, name="ix_i"),
+                                          _ptr(Y, self.dtype, "Y"), n, ib))
+
+    # -- full batch ---------------------------------------------------------------------------------
+    def step_full(self, niter=1):
+        _lib.check(self._lib.hpf_step_full(self._h, int(niter)))
+
+    def sweep(self):
+        _lib.check(self._lib.hpf_sweep(self._h))
+
+    def update_users(self):
+        _lib.check(self._lib.hpf_update_users(self._h))
+
+    def update_items(self):
+        _lib.check(self._lib.hpf_update_items(self._h))
+
+    def partials(self):
+        """(item_sums_ptr, count, theta_colsum_ptr, count): raw device pointers for the all-reduce."""
+        p1, n1, p2, n2 = ctypes.c_void_p(), ctypes.c_int64(), ctypes.c_void_p(), ctypes.c_int64()
+        _lib.check(self._lib.hpf_partials(self._h, ctypes.byref(p1), ctypes.byref(n1), ctypes.byref(p2),
+                                          ctypes.byref(n2)))
+        return p1.value, n1.value, p2.value, n2.value
+
+    # -- minibatch ----------------------------------------------------------------------------------
+    def step_batch(self, ix_u, ix_i, Y, users, items, user_batch, rho, mult, blend_all_rates):
+        ib = _index_bytes(ix_u)
+        for arr in (ix_i, users, items):
+            if _index_bytes(arr) != ib:
+                raise ValueError("all index arrays of a minibatch must have the same integer width")
+        _lib.check(self._lib.hpf_step_batch(
+            self._h, _ptr(ix_u, name="ix_u"), _ptr(ix_i, name="ix_i"), _ptr(Y, self.dtype, "Y"), int(Y.shape[0]),
+            _ptr(users, name="users"), int(users.shape[0]), _ptr(items, name="items"), int(items.shape[0]),
+            ib, int(bool(user_batch)), float(rho), float(mult), int(bool(blend_all_rates))))
+
+    # -- metrics / scoring --------------------------------------------------------------------------
+    def llk(self, ix_u, ix_i, Y, full_llk=False):
+        out = (ctypes.c_double * 4)()
+        _lib.check(self._lib.hpf_llk(self._h, _ptr(ix_u), _ptr(ix_i), _ptr(Y, self.dtype, "Y"), int(Y.shape[0]),
+                                     _index_bytes(ix_u), int(bool(full_llk)), out))
+        return list(out)
+
+    def llk_train(self, full_llk=False):
+        out = (ctypes.c_double * 4)()
+        _lib.check(self._lib.hpf_llk_train(self._h, int(bool(full_llk)), out))
+        return list(out)
+
+    def predict(self, ix_u, ix_i, out=None):
+        n = int(ix_u.shape[0])
+        if out is None:
+            out = np.empty(n, dtype=self.dtype)
+        _lib.check(self._lib.hpf_predict(self._h, _ptr(ix_u), _ptr(ix_i), n, _index_bytes(ix_u),
+                                         _ptr(out, self.dtype, "out")))
+        return out
+
+
+def update_shapes(G_sh, G_rt, L_sh, L_rt, Y, ix_u, ix_i, a, c, phi=None, device=0):
+    """Stateless fused update_phi + update_G_n_L_sh (reference pxi:551 + pxi:613) on caller buffers:
+    G_sh / L_sh are overwritten with a + sum(phi), c + sum(phi); optional phi (nY x k) is filled."""
+    lib = _lib.load()
+    dt = G_sh.dtype if isinstance(G_sh, np.ndarray) else None
+    rb = G_sh.dtype.itemsize if isinstance(G_sh, np.ndarray) else G_sh.element_size()
+    _lib.check(lib.hpf_update_shapes(rb, _index_bytes(ix_u), int(device), _ptr(G_sh, dt), _ptr(G_rt, dt),
+                                     _ptr(L_sh, dt), _ptr(L_rt, dt), _ptr(phi, dt), _ptr(Y, dt), _ptr(ix_u),
+                                     _ptr(ix_i), int(G_sh.shape[0]), int(L_sh.shape[0]), int(Y.shape[0]),
+                                     int(G_sh.shape[1]), float(a), float(c)))
+
+
+def digamma(x, device=0):
+    """The engine's device digamma (for validation against scipy.special.psi)."""
+    lib = _lib.load()
+    x = np.ascontiguousarray(x)
+    out = np.empty_like(x)
+    _lib.check(lib.hpf_digamma(x.dtype.itemsize, int(device), _ptr(x), _ptr(out), int(x.size)))
+    return out

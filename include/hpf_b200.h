@@ -1,0 +1,152 @@
+/*
+ * hpf_b200.h -- C ABI of the B200-native coordinate-ascent engine for Hierarchical Poisson
+ * Factorization (drop-in for the variational hot path of david-cortes/hpfrec).
+ *
+ * The reference has no C header: its hot path is a set of Cython `cdef ... noexcept nogil` loops
+ * (L1) driven by Cython `def` procedures (L2) in hpfrec/cython_loops.pxi ("pxi" below), reached from
+ * Python through the module-level callables of hpfrec.cython_loops_{float,double}.  Every entry
+ * point here names the reference interface it replaces.  All pointers are plain C pointers; sizes
+ * are 64-bit; no torch / C++ types cross this boundary.  Every function returns 0 on success and a
+ * non-zero HPF_E* code on failure; hpf_last_error() gives the message of the calling thread's last
+ * failure.  `real_bytes` selects the instantiation exactly like the reference's two modules do:
+ * 4 = float (cython_float.pxi:9-10), 8 = double (cython_double.pxi:7-8).  Index arrays may be
+ * 4-byte (int32) or 8-byte (the reference's `size_t ind_type`, cython_*_nonwindows.pyx:8).
+ *
+ * Pointer arguments marked [h|d] may be host or device pointers (resolved with
+ * cudaPointerGetAttributes); copies are issued on the engine's stream.
+ */
+#ifndef HPF_B200_H
+#define HPF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HPF_OK 0
+#define HPF_EINVAL 1   /* bad argument                                   */
+#define HPF_ECUDA 2    /* a CUDA runtime call / kernel launch failed     */
+#define HPF_ESTATE 3   /* call sequence error (e.g. step before load)    */
+#define HPF_ENOMEM 4   /* device allocation failed                       */
+
+typedef struct hpf_engine hpf_engine;
+
+/* ---- life cycle ------------------------------------------------------------------------- */
+
+/* Version of this ABI (bumped on incompatible change). */
+int hpf_abi_version(void);
+const char* hpf_last_error(void);
+
+/* Allocates device state for an (nU x k) user side and an (nI x k) item side on CUDA device
+ * `device`.  Owns: Gamma_shp/Gamma_rte (nU x ld), Lambda_shp/Lambda_rte (nI x ld), k_rte (nU),
+ * t_rte (nI) -- the six arrays `fit_hpf` allocates at pxi:179-181 -- plus engine-private buffers.
+ * `nU` may be a *local* user-row slice when the caller shards users across processes. */
+int hpf_create(hpf_engine** out, int64_t nU, int64_t nI, int32_t k, int32_t real_bytes, int32_t device);
+int hpf_destroy(hpf_engine* h);
+
+/* Hyper-parameters a, a', b', c, c', d' (arguments 1-6 of fit_hpf, pxi:147-148). */
+int hpf_set_hyper(hpf_engine* h, double a, double a_prime, double b_prime,
+                  double c, double c_prime, double d_prime);
+/* The derived constants exactly as the Cython partial_fit receives them (pxi:429-430: add_k_rte,
+ * add_t_rte, a, c, k_shp, t_shp); overrides what hpf_set_hyper derived. */
+int hpf_set_constants(hpf_engine* h, double a, double c, double k_shp, double t_shp,
+                      double add_k_rte, double add_t_rte);
+/* CUDA stream (cudaStream_t) all engine work is issued on; default: the legacy default stream. */
+int hpf_set_stream(hpf_engine* h, void* cuda_stream);
+/* Tunables: "panel_mb" (L2 panel size of the gathered factor side), "chunk" (nnz per lane group),
+ * "use_graph" (0/1: replay one CAVI iteration as a CUDA graph), "sweep" (0 = two-pass segmented,
+ * 1 = single-pass COO atomics), "timing" (0/1: per-kernel CUDA-event timing, see hpf_phase_ms). */
+int hpf_set_option(hpf_engine* h, const char* name, double value);
+
+/* ---- state ------------------------------------------------------------------------------ */
+
+/* Uploads the variational state (the tuple initialize_parameters returns, pxi:143; C-contiguous
+ * (n x k) matrices and length-n vectors of `real`).  [h|d] */
+int hpf_load_state(hpf_engine* h, const void* Gamma_shp, const void* Gamma_rte,
+                   const void* Lambda_shp, const void* Lambda_rte,
+                   const void* k_rte, const void* t_rte);
+/* Downloads state and/or expectations; any pointer may be NULL.  Theta = Gamma_shp/Gamma_rte
+ * (pxi:251), Beta = Lambda_shp/Lambda_rte (pxi:256).  Synchronises the stream.  [h|d] */
+int hpf_export_state(hpf_engine* h, void* Gamma_shp, void* Gamma_rte, void* Lambda_shp,
+                     void* Lambda_rte, void* k_rte, void* t_rte, void* Theta, void* Beta);
+
+/* ---- data ------------------------------------------------------------------------------- */
+
+/* Uploads the observed triples (arguments Y, ix_u, ix_i of fit_hpf, pxi:149-151) and builds the
+ * two device orderings the sweep streams (user-major and item-major, L2-panelled).  ix_u must
+ * already be local to this engine's user slice.  [h|d] */
+int hpf_load_coo(hpf_engine* h, const void* ix_u, const void* ix_i, const void* Y,
+                 int64_t nnz, int32_t index_bytes);
+
+/* ---- full-batch CAVI (replaces the loop body pxi:230-259) -------------------------------- */
+
+/* Runs `niter` complete iterations: update_phi (pxi:551) fused with update_G_n_L_sh (pxi:613),
+ * then the closed-form rate updates pxi:236, 251, 255-259, all on device. */
+int hpf_step_full(hpf_engine* h, int32_t niter);
+
+/* The same iteration split at its only cross-shard dependency, for user-sharded multi-GPU runs
+ * (SURVEY §8e).  Call order per iteration:
+ *   hpf_sweep            passes A+B; fills the user-side sums and the item-side PARTIAL sums
+ *   hpf_update_users     Gamma_shp/Gamma_rte/k_rte of the local users + local column sums of Theta
+ *   <caller all-reduces (SUM) the two buffers returned by hpf_partials over all shards>
+ *   hpf_update_items     Lambda_shp/Lambda_rte/t_rte, identical on every shard
+ * Device pointers: item_sums = (nI x ld) `real`; theta_colsum = k doubles. */
+int hpf_sweep(hpf_engine* h);
+int hpf_update_users(hpf_engine* h);
+int hpf_update_items(hpf_engine* h);
+int hpf_partials(hpf_engine* h, void** item_sums, int64_t* item_sums_count, void** theta_colsum,
+                 int64_t* theta_colsum_count);
+
+/* ---- minibatch step (replaces Cython partial_fit pxi:423-473 and the SVI epoch bodies
+ *      pxi:275-325 / 329-377) -------------------------------------------------------------- */
+
+/* One minibatch update on explicit COO triples.  users/items = the unique ids present in the batch
+ * (`users_this_batch`, `items_this_batch`), rho = step_size_batch, mult = multiplier_batch,
+ * user_batch != 0 for a batch of users.  blend_all_rates != 0 reproduces partial_fit (k_rte/t_rte
+ * blended over ALL rows, pxi:472-473); 0 reproduces the SVI epochs inside fit_hpf (batch rows
+ * only, pxi:324-325, 376-377).  [h|d] */
+int hpf_step_batch(hpf_engine* h, const void* ix_u, const void* ix_i, const void* Y, int64_t nnz,
+                   const void* users, int64_t n_users, const void* items, int64_t n_items,
+                   int32_t index_bytes, int32_t user_batch, double rho, double mult,
+                   int32_t blend_all_rates);
+
+/* ---- convergence metrics and scoring --------------------------- */
+
+/* llk_plus_rmse (pxi:627) over the given triples using the engine's current Theta/Beta:
+ * out[0] = sum_n Y*log(yhat) [- lgamma(Y+1) if full_llk], out[1] = sum_n (Y - yhat)^2,
+ * out[2] = sum_n yhat (sum_prediction, pxi:816), out[3] = sum_j (sum_u Theta_uj)(sum_i Beta_ij)
+ * (the all-pairs shortcut of pxi:78).  Accumulated in double.  [h|d] */
+int hpf_llk(hpf_engine* h, const void* ix_u, const void* ix_i, const void* Y, int64_t nnz,
+            int32_t index_bytes, int32_t full_llk, double out[4]);
+/* Same on the training triples already resident from hpf_load_coo. */
+int hpf_llk_train(hpf_engine* h, int32_t full_llk, double out[4]);
+/* predict_multiple (pxi:803): out[n] = Theta[ix_u[n]] . Beta[ix_i[n]].  [h|d] */
+int hpf_predict(hpf_engine* h, const void* ix_u, const void* ix_i, int64_t n, int32_t index_bytes,
+                void* out);
+
+/* ---- stateless one-shot forms over caller buffers ([h|d]) of the reference's L1 loops ------ */
+
+/* update_phi (pxi:551-553) + update_G_n_L_sh (pxi:613-615) fused: on return G_sh/L_sh hold
+ * a + sum phi and c + sum phi (the state after pxi:239-249).  phi may be NULL; if not it receives the
+ * (nY x k) multinomial parameters exactly as update_phi writes them. */
+int hpf_update_shapes(int32_t real_bytes, int32_t index_bytes, int32_t device,
+                      void* G_sh, const void* G_rt, void* L_sh, const void* L_rt, void* phi,
+                      const void* Y, const void* ix_u, const void* ix_i,
+                      int64_t nU, int64_t nI, int64_t nY, int32_t k, double a, double c);
+
+/* Device digamma used by the engine, exposed for validation against scipy.special.psi. [h|d] */
+int hpf_digamma(int32_t real_bytes, int32_t device, const void* x, void* out, int64_t n);
+
+/* Counters for bench/telemetry: number of kernels this engine has launched so far. */
+int hpf_launch_count(hpf_engine* h, int64_t* out);
+/* With option "timing"=1: accumulated device milliseconds of the four kernels of a full-batch
+ * iteration since the option was set: [item-major pass, user-major pass, user update, item update]. */
+int hpf_phase_ms(hpf_engine* h, double out[4], int64_t* iterations);
+/* Leading dimension (padded k) of the engine's device matrices. */
+int hpf_ld(hpf_engine* h, int32_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HPF_B200_H */

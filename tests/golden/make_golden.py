@@ -1,0 +1,130 @@
+#!/usr/bin/env python3
+"""Generates tests/golden/*.npz from the UNMODIFIED compiled reference (oracle/_ref, built from
+/root/reference by oracle/build_ref.py).  Run in the build container:
+
+    python oracle/build_ref.py && python tests/golden/make_golden.py
+
+The reference ships no golden vectors of its own, so these are "outputs of the
+reference itself run here".  Versions that pin them (recorded in every file): numpy, scipy, cython.
+Everything is fp64, ncores=1, allow_inconsistent_math=False (par_sh=0) unless noted.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import hpf_oracle as O  # noqa: E402
+from oracle import ref_loader as R  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+KEYS = ("Theta", "Beta", "Gamma_shp", "Gamma_rte", "Lambda_shp", "Lambda_rte", "k_rte", "t_rte")
+
+
+def versions():
+    import scipy, Cython
+    return "numpy %s scipy %s cython %s" % (np.__version__, scipy.__version__, Cython.__version__)
+
+
+def toy():
+    df = O.readme_toy()
+    return (df.UserId.to_numpy().astype(np.int64), df.ItemId.to_numpy().astype(np.int64),
+            df.Count.to_numpy().astype(np.float64))
+
+
+def main():
+    mod = R.load(False)
+    modf = R.load(True)
+    assert mod is not None, "build oracle/_ref first"
+    u, i, y = toy()
+    nU = nI = 100
+    k = 10
+    ver = versions()
+
+    # --- full batch trajectory on the README toy (config C1) ---------------------------------
+    full = {"versions": ver, "ix_u": u, "ix_i": i, "Y": y}
+    for its in (1, 2, 10, 100):
+        r = R.ref_fit_hpf(mod, y, u, i, nU, nI, k, its, seed=123)
+        for key in KEYS:
+            full["it%d_%s" % (its, key)] = r[key]
+        full["it%d_niter" % its] = r["niter"]
+    # float build, 1 and 10 iterations (the fp32 engine is gated on single-sweep parity)
+    for its in (1, 10):
+        r = R.ref_fit_hpf(modf, y.astype(np.float32), u, i, nU, nI, k, its, seed=123)
+        for key in ("Theta", "Beta"):
+            full["f32_it%d_%s" % (its, key)] = r[key]
+    # llk / predictions at the 100-iteration state
+    r = R.ref_fit_hpf(mod, y, u, i, nU, nI, k, 100, seed=123)
+    ind = mod.obj_ind_type
+    full["llk_full"] = np.float64(mod.calc_llk(y, u.astype(ind), i.astype(ind), r["Theta"], r["Beta"], k, 1, 1))
+    full["llk_part"] = np.float64(mod.calc_llk(y, u.astype(ind), i.astype(ind), r["Theta"], r["Beta"], k, 1, 0))
+    full["pred"] = mod.predict_arr(r["Theta"], r["Beta"], u.astype(ind), i.astype(ind), 1)
+    np.savez_compressed(os.path.join(OUT, "toy_full.npz"), **full)
+
+    # --- odd shapes: k not a multiple of the pack, empty users/items, ragged degrees ------------
+    rng = np.random.default_rng(7)
+    nU2, nI2, k2 = 37, 53, 7
+    uu = rng.integers(0, nU2 - 3, size=400)      # last 3 users have no data
+    ii = rng.integers(2, nI2, size=400)          # first 2 items have no data
+    key = np.unique(uu * nI2 + ii)
+    uu, ii = key // nI2, key % nI2
+    perm = rng.permutation(uu.shape[0])
+    uu, ii = uu[perm], ii[perm]
+    yy = (1 + rng.poisson(1.5, size=uu.shape[0])).astype(np.float64)
+    odd = {"versions": ver, "ix_u": uu, "ix_i": ii, "Y": yy, "nU": nU2, "nI": nI2, "k": k2}
+    for its in (1, 25):
+        r = R.ref_fit_hpf(mod, yy, uu, ii, nU2, nI2, k2, its, seed=5, a=0.5, a_prime=0.4, b_prime=1.3,
+                          c=0.6, c_prime=0.2, d_prime=0.8)
+        for key_ in KEYS:
+            odd["it%d_%s" % (its, key_)] = r[key_]
+    np.savez_compressed(os.path.join(OUT, "odd_full.npz"), **odd)
+
+    # --- SVI inside fit_hpf (sorted by user; ncores=1) -----------------------------------------
+    order = np.argsort(u, kind="stable")
+    us, is_, ys = u[order], i[order], y[order]
+    st = np.zeros(nU + 1, dtype=np.int64)
+    np.add.at(st, us + 1, 1)
+    st = np.cumsum(st)
+    svi = {"versions": ver, "ix_u": us, "ix_i": is_, "Y": ys, "st_ix_u": st}
+    for name, upb, ipb in (("users", 20, 0), ("items", 0, 30), ("both", 20, 30)):
+        r = R.ref_fit_hpf(mod, ys, us, is_, nU, nI, k, 8, seed=123, users_per_batch=upb, items_per_batch=ipb,
+                          st_ix_u=st, par_sh=1, ncores=1)
+        for key_ in KEYS:
+            svi["%s_%s" % (name, key_)] = r[key_]
+    np.savez_compressed(os.path.join(OUT, "toy_svi.npz"), **svi)
+
+    # --- Cython-level partial_fit: five mixed calls on a fresh state ---------------------------
+    Theta = np.empty((nU, k))
+    Beta = np.empty((nI, k))
+    Gs, Gr, Ls, Lr, kr, tr = mod.initialize_parameters(Theta, Beta, 123, 0.3, 0.3, 1.0, 0.3, 0.3, 1.0)
+    pf = {"versions": ver}
+    rngb = np.random.default_rng(11)
+    a = c = 0.3
+    k_shp = 0.3 + k * 0.3
+    t_shp = 0.3 + k * 0.3
+    for call, kind in enumerate(("users", "items", "users", "users", "items")):
+        if kind == "users":
+            ids = np.unique(rngb.integers(0, nU, size=20))
+            sel = np.isin(u, ids)
+        else:
+            ids = np.unique(rngb.integers(0, nI, size=25))
+            sel = np.isin(i, ids)
+        ub, ib, yb = u[sel], i[sel], y[sel]
+        users, items = np.unique(ub), np.unique(ib)
+        rho = 1.0 if call == 0 else 1 / np.sqrt(call + 2)
+        mult = float(nU) / users.shape[0]
+        mod.partial_fit(yb, ub.astype(ind), ib.astype(ind), Theta, Beta, Gs, Gr, Ls, Lr, kr, tr,
+                        0.3 / 1.0, 0.3 / 1.0, a, c, k_shp, t_shp, k, users.astype(ind), items.astype(ind), 0,
+                        rho, mult, 1, kind == "users")
+        pf["call%d_kind" % call] = kind
+        pf["call%d_ids" % call] = ids
+        pf["call%d_rho" % call] = rho
+        for key_, arr in zip(KEYS, (Theta, Beta, Gs, Gr, Ls, Lr, kr, tr)):
+            pf["call%d_%s" % (call, key_)] = arr.copy()
+    np.savez_compressed(os.path.join(OUT, "toy_partial_fit.npz"), **pf)
+    print("golden files written to", OUT, "|", ver)
+
+
+if __name__ == "__main__":
+    main()
