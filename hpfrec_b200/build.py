@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
-LIB = os.path.join(OUT_DIR, "libhpf_b200.so")
+LIB = os.path.join(OUT_DIR, "libhpf_b200_tune.so" if os.environ.get("HPF_TUNE") else "libhpf_b200.so")
 SOURCES = ["hpf_engine.cu"]
 DEPS = ["hpf_engine.cu", "hpf_kernels.cuh", "hpf_batch.cuh", "hpf_device.cuh", "hpf_batch_host.inl",
         os.path.join("..", "..", "include", "hpf_b200.h")]
@@ -23,7 +23,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr", "--extended-lambda",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-shared",
     "-Xptxas", "-v" if os.environ.get("HPF_PTXAS_V") else "-O3",
-]
+] + (["-DHPF_TUNE"] if os.environ.get("HPF_TUNE") else [])
 
 
 def find_nvcc():

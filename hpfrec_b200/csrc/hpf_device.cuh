@@ -44,6 +44,43 @@ __device__ __forceinline__ void st_pack(real* p, const Pack<real>& r) {
     *reinterpret_cast<int4*>(p) = *reinterpret_cast<const int4*>(&r);
 }
 
+// L2 residency control: the gathered factor panel is loaded with an evict_last policy, the
+// streamed triples with evict_first, so the stream does not push the panel out of the 126 MB L2.
+__device__ __forceinline__ uint64_t l2_policy_keep() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_stream() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+template <typename real>
+__device__ __forceinline__ Pack<real> ldg_pack_hint(const real* p, uint64_t pol) {
+    Pack<real> r;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&r);
+    asm volatile("ld.global.nc.L2::cache_hint.v4.b32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])
+                 : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ int ldg_stream(const int* p, uint64_t pol) {
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ float ldg_stream(const float* p, uint64_t pol) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ double ldg_stream(const double* p, uint64_t pol) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
 // vector reduction into global memory: RED.E.ADD.F32x4 (sm_90+) for float, 2x RED.E.ADD.F64 for double
 __device__ __forceinline__ void red_add_pack(float* p, const Pack<float>& r) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]),

@@ -107,9 +107,10 @@ struct hpf_engine {
     bool data_loaded = false;
     // options
     double panel_mb = 48.0;
-    int chunk = 128;
+    int chunk = 64;
     int sweep_mode = 0;
     int use_graph = 0;
+    int v_lpg = 0, v_unroll = 0, v_minb = 0, v_hint = 0;  // sweep-kernel variant (tuning builds only)
     int64_t launches = 0;
     cudaGraphExec_t graph_lean = nullptr, graph_mat = nullptr;
     // optional per-kernel timing of full-batch iterations
@@ -296,19 +297,78 @@ int build_order(hpf_engine* h, const int* major, const int* minor, const real* v
 }
 
 // ---- kernel launch wrappers -----------------------------------------------------------------------
-template <typename C>
-int launch_sweep_major(hpf_engine* h, const int* row, const int* col, const void* val, const void* xown,
-                       const void* xgat, void* acc) {
-    using real = typename C::real;
-    if (h->nnz == 0) return HPF_OK;
+template <typename real, int LPG, int VPL, int UNROLL, int MINB, int HINT, int FUSE = 0>
+int launch_sweep_variant(hpf_engine* h, const int* row, const int* col, const void* val, const void* xown,
+                         const void* xgat, void* acc, void* acc_minor = nullptr) {
     const long long groups = (h->nnz + h->chunk - 1) / h->chunk;
-    const long long threads = groups * C::lpg;
-    constexpr int UNROLL = 4;
-    hpf::sweep_major_kernel<real, C::lpg, C::vpl, UNROLL><<<nblk(threads), 256, 0, h->stream>>>(
-        row, col, (const real*)val, h->nnz, h->chunk, (const real*)xown, (const real*)xgat, (real*)acc, h->ld);
+    const long long threads = groups * LPG;
+    hpf::sweep_major_kernel<real, LPG, VPL, UNROLL, MINB, HINT, FUSE><<<nblk(threads), 256, 0, h->stream>>>(
+        row, col, (const real*)val, h->nnz, h->chunk, (const real*)xown, (const real*)xgat, (real*)acc,
+        (real*)acc_minor, h->ld);
     h->launches++;
     CKK();
     return HPF_OK;
+}
+
+// Sweep-kernel shape.  The default (lane-group width, unroll, min blocks/SM, L2 hints) per row length
+// comes from measurements on B200 (profiles/); with -DHPF_TUNE every combination is compiled and the
+// "lpg"/"unroll"/"minb"/"hint" options select one at run time (tools/tune_sweep.py).
+template <typename C>
+int launch_sweep_major(hpf_engine* h, const int* row, const int* col, const void* val, const void* xown,
+                       const void* xgat, void* acc, void* acc_minor = nullptr) {
+    using real = typename C::real;
+    if (h->nnz == 0) return HPF_OK;
+#ifdef HPF_TUNE
+    if (acc_minor != nullptr) {
+        constexpr int packs_f = C::lpg * C::vpl;
+        const int lpg_f = h->v_lpg ? h->v_lpg : C::lpg, mb_f = h->v_minb ? h->v_minb : 3, hint_f = h->v_hint;
+#define HPF_F(L, M, H)                                  \
+    if (lpg_f == L && mb_f == M && hint_f == H)         \
+        return launch_sweep_variant<real, L, packs_f / L, 1, M, H, 1>(h, row, col, val, xown, xgat, acc, acc_minor);
+        if constexpr (packs_f == 16 && sizeof(real) == 4) {
+            HPF_F(4, 3, 0) HPF_F(4, 3, 1) HPF_F(8, 3, 0) HPF_F(8, 3, 1) HPF_F(8, 4, 0) HPF_F(8, 4, 1) HPF_F(4, 2, 0) HPF_F(8, 2, 0)
+        }
+#undef HPF_F
+        return fail(HPF_EINVAL, "no such fused sweep variant");
+    }
+#endif
+#ifdef HPF_TUNE
+    constexpr int packs = C::lpg * C::vpl;  // 16-byte packs per padded row handled by the default shape
+    const int lpg = h->v_lpg ? h->v_lpg : C::lpg, un = h->v_unroll ? h->v_unroll : 4;
+    const int mb = h->v_minb ? h->v_minb : 2, hint = h->v_hint;
+#define HPF_V(L, U, M, H)                                                          \
+    if (lpg == L && un == U && mb == M && hint == H)                               \
+        return launch_sweep_variant<real, L, packs / L, U, M, H>(h, row, col, val, xown, xgat, acc);
+#define HPF_VL(L)                                                                  \
+    HPF_V(L, 1, 2, 0) HPF_V(L, 2, 2, 0) HPF_V(L, 4, 2, 0) HPF_V(L, 1, 3, 0) HPF_V(L, 2, 3, 0) HPF_V(L, 4, 3, 0) \
+    HPF_V(L, 1, 4, 0) HPF_V(L, 2, 4, 0) HPF_V(L, 4, 4, 0) HPF_V(L, 1, 2, 1) HPF_V(L, 2, 2, 1) HPF_V(L, 4, 2, 1) \
+    HPF_V(L, 1, 3, 1) HPF_V(L, 2, 3, 1) HPF_V(L, 4, 3, 1) HPF_V(L, 1, 4, 1) HPF_V(L, 2, 4, 1) HPF_V(L, 4, 4, 1)
+    if constexpr (packs == 16 && sizeof(real) == 4) {
+        HPF_VL(4) HPF_VL(8) HPF_VL(16)
+    }
+    if constexpr (packs == 8 && sizeof(real) == 4) {
+        HPF_VL(4) HPF_VL(8)
+    }
+    if constexpr (packs == 32 && sizeof(real) == 4) {
+        HPF_VL(8) HPF_VL(16) HPF_VL(32)
+    }
+#undef HPF_VL
+#undef HPF_V
+    return fail(HPF_EINVAL, "no such sweep variant (lpg=%d unroll=%d minb=%d hint=%d)", lpg, un, mb, hint);
+#else
+    // Measured on B200 (profiles/r01_tune_*.jsonl, 1M x 380K x 48M nnz): narrow lane groups with no
+    // unrolling and 3-4 resident CTAs/SM beat wider groups / deeper unrolling at every row length.
+    constexpr int packs = C::lpg * C::vpl;
+    if (acc_minor != nullptr) {  // one-pass mode ("sweep"=2)
+        if constexpr (packs <= 8) return launch_sweep_variant<real, 8, 1, 1, 3, 0, 1>(h, row, col, val, xown, xgat, acc, acc_minor);
+        else if constexpr (packs <= 16) return launch_sweep_variant<real, 8, 2, 1, 3, 0, 1>(h, row, col, val, xown, xgat, acc, acc_minor);
+        else return launch_sweep_variant<real, C::lpg, C::vpl, 1, 2, 0, 1>(h, row, col, val, xown, xgat, acc, acc_minor);
+    }
+    if constexpr (packs <= 8) return launch_sweep_variant<real, 4, 2, 1, 2, 0>(h, row, col, val, xown, xgat, acc);
+    else if constexpr (packs <= 16) return launch_sweep_variant<real, 4, 4, 1, 3, 1>(h, row, col, val, xown, xgat, acc);
+    else if constexpr (packs <= 32) return launch_sweep_variant<real, 8, 4, 1, 4, 0>(h, row, col, val, xown, xgat, acc);
+    else return launch_sweep_variant<real, C::lpg, C::vpl, 1, 2, 0>(h, row, col, val, xown, xgat, acc);
+#endif
 }
 
 template <typename C>
@@ -406,6 +466,12 @@ int do_sweep(hpf_engine* h) {
             TRY(launch_sweep_coo<C>(h, h->A_row, h->A_col, h->A_val, h->nnz, h->xu, h->xi, h->accU, h->accI,
                                     h->ld, nullptr, h->k, h->stream));
             mark(h, 1);
+            mark(h, 2);
+            return HPF_OK;
+        }
+        if (h->sweep_mode == 2) {  // one fused user-major pass (gathers + REDs)
+            mark(h, 1);
+            TRY(launch_sweep_major<C>(h, h->A_row, h->A_col, h->A_val, h->xu, h->xi, h->accU, h->accI));
             mark(h, 2);
             return HPF_OK;
         }
@@ -606,6 +672,16 @@ int hpf_set_option(hpf_engine* h, const char* name, double value) {
     } else if (!strcmp(name, "sweep")) {
         h->sweep_mode = (int)value;
         drop_graphs(h);
+    } else if (!strcmp(name, "lpg") || !strcmp(name, "unroll") || !strcmp(name, "minb") || !strcmp(name, "hint")) {
+#ifndef HPF_TUNE
+        return fail(HPF_EINVAL, "option '%s' needs a library built with -DHPF_TUNE", name);
+#else
+        if (!strcmp(name, "lpg")) h->v_lpg = (int)value;
+        if (!strcmp(name, "unroll")) h->v_unroll = (int)value;
+        if (!strcmp(name, "minb")) h->v_minb = (int)value;
+        if (!strcmp(name, "hint")) h->v_hint = (int)value;
+        drop_graphs(h);
+#endif
     } else if (!strcmp(name, "use_graph")) {
         h->use_graph = (int)value;
     } else if (!strcmp(name, "timing")) {

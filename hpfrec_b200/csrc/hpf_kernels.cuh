@@ -23,12 +23,15 @@ namespace hpf {
 //     (row, chunk) segment, not once per nnz).
 //       acc[r, :] += sum_{n in segment} (Y[n] / dot(xown[r], xgat[c_n])) * xgat[c_n, :]
 // =============================================================================================
-template <typename real, int LPG, int VPL, int UNROLL>
-__global__ void __launch_bounds__(256)
+//     FUSE=1 ("one-pass" mode): the same walk also pushes w_n * xown[r,:] into the MINOR side's sums
+//     with one vector RED per pack per nnz, so a single user-major pass produces both shape matrices;
+//     gathers ride the L2->SM response path and the REDs the SM->L2 request path.
+template <typename real, int LPG, int VPL, int UNROLL, int MINB, int HINT, int FUSE>
+__global__ void __launch_bounds__(256, MINB)
 sweep_major_kernel(const int* __restrict__ row, const int* __restrict__ col,
                    const real* __restrict__ val, long long nnz, int chunk,
                    const real* __restrict__ xown, const real* __restrict__ xgat,
-                   real* __restrict__ acc, int ld) {
+                   real* __restrict__ acc, real* __restrict__ acc_minor, int ld) {
     constexpr int EPV = Pack<real>::N;
     static_assert(LPG % UNROLL == 0, "UNROLL must divide LPG");
     const int gl = (threadIdx.x & 31) % LPG;
@@ -37,6 +40,11 @@ sweep_major_kernel(const int* __restrict__ row, const int* __restrict__ col,
     if (beg >= nnz) return;  // whole groups leave together; shuffles below use the group mask
     const long long end = (beg + chunk < nnz) ? beg + chunk : nnz;
     const unsigned gmask = group_mask<LPG>();
+    uint64_t pol_keep = 0, pol_stream = 0;
+    if (HINT) {
+        pol_keep = l2_policy_keep();
+        pol_stream = l2_policy_stream();
+    }
 
     int off[VPL];
     bool act[VPL];
@@ -53,31 +61,55 @@ sweep_major_kernel(const int* __restrict__ row, const int* __restrict__ col,
     }
     int cur = -1;
 
+    // coalesced fetch of LPG triples (one per lane), software-pipelined one batch ahead
+    int r = -1, c = 0;
+    real y = real(0);
+    if (beg + gl < end) {
+        if (HINT) {
+            r = ldg_stream(row + beg + gl, pol_stream);
+            c = ldg_stream(col + beg + gl, pol_stream);
+            y = ldg_stream(val + beg + gl, pol_stream);
+        } else {
+            r = __ldg(row + beg + gl);
+            c = __ldg(col + beg + gl);
+            y = __ldg(val + beg + gl);
+        }
+    }
     for (long long base = beg; base < end; base += LPG) {
-        // coalesced fetch of LPG triples (one per lane), broadcast inside the group below
-        const long long idx = base + gl;
-        int r = -1, c = 0;
-        real y = real(0);
-        if (idx < end) {
-            r = __ldg(row + idx);
-            c = __ldg(col + idx);
-            y = __ldg(val + idx);
+        int rn = -1, cn = 0;
+        real yn = real(0);
+        const long long nidx = base + LPG + gl;
+        if (nidx < end) {
+            if (HINT) {
+                rn = ldg_stream(row + nidx, pol_stream);
+                cn = ldg_stream(col + nidx, pol_stream);
+                yn = ldg_stream(val + nidx, pol_stream);
+            } else {
+                rn = __ldg(row + nidx);
+                cn = __ldg(col + nidx);
+                yn = __ldg(val + nidx);
+            }
         }
 #pragma unroll
         for (int t0 = 0; t0 < LPG; t0 += UNROLL) {
             if (base + t0 >= end) break;  // uniform inside the group
             Pack<real> g[UNROLL][VPL];
-            int rr[UNROLL];
+            int rr[UNROLL], ccs[UNROLL];
             real yy[UNROLL];
 #pragma unroll
             for (int q = 0; q < UNROLL; ++q) {
                 const int cc = __shfl_sync(gmask, c, t0 + q, LPG);
+                ccs[q] = cc;
                 rr[q] = __shfl_sync(gmask, r, t0 + q, LPG);
                 yy[q] = __shfl_sync(gmask, y, t0 + q, LPG);
                 const real* src = xgat + (size_t)cc * ld;
 #pragma unroll
-                for (int v = 0; v < VPL; ++v)
-                    g[q][v] = act[v] ? ldg_pack(src + off[v]) : pack_zero<real>();
+                for (int v = 0; v < VPL; ++v) {
+                    if (HINT)
+                        g[q][v] = act[v] ? ldg_pack_hint(src + off[v], pol_keep) : pack_zero<real>();
+                    else
+                        g[q][v] = act[v] ? ldg_pack(src + off[v]) : pack_zero<real>();
+                }
             }
 #pragma unroll
             for (int q = 0; q < UNROLL; ++q) {
@@ -106,8 +138,21 @@ sweep_major_kernel(const int* __restrict__ row, const int* __restrict__ col,
                 for (int v = 0; v < VPL; ++v)
 #pragma unroll
                     for (int e = 0; e < EPV; ++e) sum[v].v[e] = fma(w, g[q][v].v[e], sum[v].v[e]);
+                if (FUSE) {
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) {
+                        if (!act[v]) continue;
+                        Pack<real> p;
+#pragma unroll
+                        for (int e = 0; e < EPV; ++e) p.v[e] = w * own[v].v[e];
+                        red_add_pack(acc_minor + (size_t)ccs[q] * ld + off[v], p);
+                    }
+                }
             }
         }
+        r = rn;
+        c = cn;
+        y = yn;
     }
     if (cur >= 0) {
 #pragma unroll
