@@ -83,7 +83,7 @@ batch_prepare_kernel(int nrows, const int* __restrict__ rows, int ld, int k, con
             const Pack<real> tv = ld_pack(rte + (size_t)r * ld + off[v]);
 #pragma unroll
             for (int e = 0; e < EPV; ++e) {
-                const real lg = (off[v] + e < k) ? digamma(sv.v[e]) - rlog(tv.v[e]) : -INFINITY;
+                const real lg = (off[v] + e < k) ? elog(sv.v[e], tv.v[e]) : -INFINITY;
                 E[v].v[e] = lg;
                 m = lg > m ? lg : m;
             }

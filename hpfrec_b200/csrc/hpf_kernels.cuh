@@ -294,10 +294,10 @@ update_rows_kernel(int nrows, int ld, int k, real* __restrict__ x, real* __restr
                 const real t_ = inv + other[v][e];
                 shp[v].v[e] = real_col ? s_ : real(0);
                 rte[v].v[e] = real_col ? t_ : real(1);
-                const real th = real_col ? s_ / t_ : real(0);
+                const real th = real_col ? rratio(s_, t_) : real(0);
                 rowsum += th;
                 csum[v][e] += th;
-                const real lg = real_col ? digamma(s_) - rlog(t_) : -INFINITY;
+                const real lg = real_col ? elog(s_, t_) : -INFINITY;
                 E[v].v[e] = lg;
                 m = lg > m ? lg : m;
             }
@@ -372,7 +372,7 @@ rows_to_x_kernel(int nrows, const int* __restrict__ rows, int ld, int k, const r
 #pragma unroll
             for (int e = 0; e < EPV; ++e) {
                 const bool real_col = off[v] + e < k;
-                const real lg = real_col ? digamma(sv.v[e]) - rlog(tv.v[e]) : -INFINITY;
+                const real lg = real_col ? elog(sv.v[e], tv.v[e]) : -INFINITY;
                 E[v].v[e] = lg;
                 m = lg > m ? lg : m;
                 if (real_col) csum[v][e] += sv.v[e] / tv.v[e];
