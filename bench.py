@@ -262,7 +262,10 @@ def run_ours(a):
         partial = hdist.engine_partial_tensors(eng, local)
 
         def steps(n):
-            hdist.run_sharded_iterations(eng, n, partial)
+            if os.environ.get("HPF_NO_OVERLAP"):
+                hdist.run_sharded_iterations(eng, n, partial)
+            else:
+                hdist.run_sharded_iterations_overlapped(eng, n, partial)
     else:
         def steps(n):
             eng.step_full(n)
@@ -340,7 +343,7 @@ def run_ours(a):
             e.load_state(*hstate)
             e.load_coo(hu, hi_, hy)
             if world > 1:
-                hdist.run_sharded_iterations(e, a.steps, hdist.engine_partial_tensors(e, local))
+                hdist.run_sharded_iterations_overlapped(e, a.steps, hdist.engine_partial_tensors(e, local))
             else:
                 e.step_full(a.steps)
             e.export_state(**out_state)

@@ -29,6 +29,7 @@ SIGNATURES = {
     "hpf_load_coo": ([_P, _P, _P, _P, _I64, _I32], _c.c_int),
     "hpf_step_full": ([_P, _I32], _c.c_int),
     "hpf_sweep": ([_P], _c.c_int),
+    "hpf_sweep_side": ([_P, _I32], _c.c_int),
     "hpf_update_users": ([_P], _c.c_int),
     "hpf_update_items": ([_P], _c.c_int),
     "hpf_partials": ([_P, _c.POINTER(_P), _c.POINTER(_I64), _c.POINTER(_P), _c.POINTER(_I64)], _c.c_int),

@@ -4,6 +4,7 @@
 #include "../../include/hpf_b200.h"
 #include "hpf_kernels.cuh"
 #include "hpf_batch.cuh"
+#include "hpf_sweep_tma.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -310,6 +311,42 @@ int launch_sweep_variant(hpf_engine* h, const int* row, const int* col, const vo
     return HPF_OK;
 }
 
+// staged-gather sweep (hpf_sweep_tma.cuh): 8 lanes per row, rows staged in shared memory by bulk copies
+template <typename real, int VPL, int MINB>
+int launch_sweep_tma_variant(hpf_engine* h, const int* row, const int* col, const void* val, const void* xown,
+                             const void* xgat, void* acc) {
+    auto kern = hpf::sweep_tma_kernel<real, VPL, MINB>;
+    const size_t smem = 8 * (32 * (size_t)h->ld * sizeof(real) + 32 * 8);
+    static thread_local size_t configured = 0;
+    if (configured < smem) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const long long groups = (h->nnz + h->chunk - 1) / h->chunk;
+    kern<<<nblk(groups * 8), 256, smem, h->stream>>>(row, col, (const real*)val, h->nnz, h->chunk, (const real*)xown,
+                                                     (const real*)xgat, (real*)acc, h->ld);
+    h->launches++;
+    CKK();
+    return HPF_OK;
+}
+
+template <typename C>
+int launch_sweep_tma(hpf_engine* h, const int* row, const int* col, const void* val, const void* xown,
+                     const void* xgat, void* acc) {
+    using real = typename C::real;
+    if (h->nnz == 0) return HPF_OK;
+    constexpr int packs = C::lpg * C::vpl;
+    if constexpr (packs > 32) {
+        return fail(HPF_EINVAL, "staged-gather sweep supports rows up to 512 bytes");
+    } else {
+        constexpr int VPL = packs <= 8 ? 1 : (packs <= 16 ? 2 : 4);
+        const int mb = h->v_minb ? h->v_minb : 3;
+        if (mb == 2) return launch_sweep_tma_variant<real, VPL, 2>(h, row, col, val, xown, xgat, acc);
+        if (mb == 4) return launch_sweep_tma_variant<real, VPL, 4>(h, row, col, val, xown, xgat, acc);
+        return launch_sweep_tma_variant<real, VPL, 3>(h, row, col, val, xown, xgat, acc);
+    }
+}
+
 // Sweep-kernel shape.  The default (lane-group width, unroll, min blocks/SM, L2 hints) per row length
 // comes from measurements on B200 (profiles/); with -DHPF_TUNE every combination is compiled and the
 // "lpg"/"unroll"/"minb"/"hint" options select one at run time (tools/tune_sweep.py).
@@ -342,7 +379,8 @@ int launch_sweep_major(hpf_engine* h, const int* row, const int* col, const void
 #define HPF_VL(L)                                                                  \
     HPF_V(L, 1, 2, 0) HPF_V(L, 2, 2, 0) HPF_V(L, 4, 2, 0) HPF_V(L, 1, 3, 0) HPF_V(L, 2, 3, 0) HPF_V(L, 4, 3, 0) \
     HPF_V(L, 1, 4, 0) HPF_V(L, 2, 4, 0) HPF_V(L, 4, 4, 0) HPF_V(L, 1, 2, 1) HPF_V(L, 2, 2, 1) HPF_V(L, 4, 2, 1) \
-    HPF_V(L, 1, 3, 1) HPF_V(L, 2, 3, 1) HPF_V(L, 4, 3, 1) HPF_V(L, 1, 4, 1) HPF_V(L, 2, 4, 1) HPF_V(L, 4, 4, 1)
+    HPF_V(L, 1, 3, 1) HPF_V(L, 2, 3, 1) HPF_V(L, 4, 3, 1) HPF_V(L, 1, 4, 1) HPF_V(L, 2, 4, 1) HPF_V(L, 4, 4, 1) \
+    HPF_V(L, 1, 2, 2) HPF_V(L, 1, 3, 2) HPF_V(L, 1, 4, 2)
     if constexpr (packs == 16 && sizeof(real) == 4) {
         HPF_VL(4) HPF_VL(8) HPF_VL(16)
     }
@@ -458,29 +496,40 @@ void mark(hpf_engine* h, int which) {
     if (h->timing && h->ev[0]) cudaEventRecord(h->ev[which], h->stream);
 }
 
-int do_sweep(hpf_engine* h) {
+// sides: bit 0 = item-major pass (item-side sums), bit 1 = user-major pass (user-side sums).  The
+// single-pass modes (1: COO atomics, 2: fused) produce both sides in the "user" call.
+int do_sweep(hpf_engine* h, int sides = 3) {
     return dispatch(h->rb, h->ld, [&](auto cfg) {
         using C = decltype(cfg);
-        mark(h, 0);
-        if (h->sweep_mode == 1) {
-            TRY(launch_sweep_coo<C>(h, h->A_row, h->A_col, h->A_val, h->nnz, h->xu, h->xi, h->accU, h->accI,
-                                    h->ld, nullptr, h->k, h->stream));
-            mark(h, 1);
-            mark(h, 2);
+        if (sides & 1) mark(h, 0);
+        if (h->sweep_mode == 1 || h->sweep_mode == 2) {
+            if (sides & 1) mark(h, 1);
+            if (sides & 2) {
+                if (h->sweep_mode == 1)
+                    TRY(launch_sweep_coo<C>(h, h->A_row, h->A_col, h->A_val, h->nnz, h->xu, h->xi, h->accU, h->accI,
+                                            h->ld, nullptr, h->k, h->stream));
+                else  // one fused user-major pass (gathers + REDs)
+                    TRY(launch_sweep_major<C>(h, h->A_row, h->A_col, h->A_val, h->xu, h->xi, h->accU, h->accI));
+                mark(h, 2);
+            }
             return HPF_OK;
         }
-        if (h->sweep_mode == 2) {  // one fused user-major pass (gathers + REDs)
+        // item-major pass first: its output (item-side partial sums) is what a multi-GPU caller
+        // all-reduces, so the reduction can overlap the user-major pass
+        if (sides & 1) {
+            if (h->sweep_mode == 3)  // staged gathers: cp.async.bulk + mbarrier ring
+                TRY(launch_sweep_tma<C>(h, h->B_row, h->B_col, h->B_val, h->xi, h->xu, h->accI));
+            else
+                TRY(launch_sweep_major<C>(h, h->B_row, h->B_col, h->B_val, h->xi, h->xu, h->accI));
             mark(h, 1);
-            TRY(launch_sweep_major<C>(h, h->A_row, h->A_col, h->A_val, h->xu, h->xi, h->accU, h->accI));
-            mark(h, 2);
-            return HPF_OK;
         }
-        // pass B first: its output (item-side partial sums) is what a multi-GPU caller all-reduces,
-        // so the reduction can overlap pass A
-        TRY(launch_sweep_major<C>(h, h->B_row, h->B_col, h->B_val, h->xi, h->xu, h->accI));
-        mark(h, 1);
-        TRY(launch_sweep_major<C>(h, h->A_row, h->A_col, h->A_val, h->xu, h->xi, h->accU));
-        mark(h, 2);
+        if (sides & 2) {
+            if (h->sweep_mode == 3)
+                TRY(launch_sweep_tma<C>(h, h->A_row, h->A_col, h->A_val, h->xu, h->xi, h->accU));
+            else
+                TRY(launch_sweep_major<C>(h, h->A_row, h->A_col, h->A_val, h->xu, h->xi, h->accU));
+            mark(h, 2);
+        }
         return HPF_OK;
     });
 }
@@ -806,6 +855,15 @@ int hpf_sweep(hpf_engine* h) {
     DeviceGuard guard(h->device);
     TRY(ensure_x(h));
     return do_sweep(h);
+}
+
+int hpf_sweep_side(hpf_engine* h, int32_t side) {
+    if (!h) return fail(HPF_EINVAL, "engine is NULL");
+    if (side != 0 && side != 1) return fail(HPF_EINVAL, "side must be 0 (items) or 1 (users)");
+    if (!h->data_loaded) return fail(HPF_ESTATE, "no data loaded (call hpf_load_coo first)");
+    DeviceGuard guard(h->device);
+    TRY(ensure_x(h));
+    return do_sweep(h, side == 0 ? 1 : 2);
 }
 
 int hpf_update_users(hpf_engine* h) {

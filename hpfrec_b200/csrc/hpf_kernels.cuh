@@ -105,7 +105,7 @@ sweep_major_kernel(const int* __restrict__ row, const int* __restrict__ col,
                 const real* src = xgat + (size_t)cc * ld;
 #pragma unroll
                 for (int v = 0; v < VPL; ++v) {
-                    if (HINT)
+                    if (HINT == 1)
                         g[q][v] = act[v] ? ldg_pack_hint(src + off[v], pol_keep) : pack_zero<real>();
                     else
                         g[q][v] = act[v] ? ldg_pack(src + off[v]) : pack_zero<real>();

@@ -80,3 +80,23 @@ def run_sharded_iterations(engine, niter, partial_tensors=None, group=None, all_
         for t in partial_tensors:
             all_reduce(t)
         engine.update_items()
+
+
+def run_sharded_iterations_overlapped(engine, niter, partial_tensors=None, group=None):
+    """Same result as run_sharded_iterations, but the all-reduce of the item-side partial sums is
+    issued asynchronously right after the item-major pass and overlaps the user-major pass and the
+    user update (the NCCL kernel runs on NCCL's stream; `work.wait()` orders the item update after
+    it on the engine's stream).  Needs an initialised process group and a real Engine."""
+    import torch.distributed as dist
+    if partial_tensors is None:
+        partial_tensors = engine_partial_tensors(engine)
+    t_items, t_theta = partial_tensors
+    for _ in range(int(niter)):
+        engine.sweep_side(0)
+        w_items = dist.all_reduce(t_items, op=dist.ReduceOp.SUM, group=group, async_op=True)
+        engine.sweep_side(1)
+        engine.update_users()
+        w_theta = dist.all_reduce(t_theta, op=dist.ReduceOp.SUM, group=group, async_op=True)
+        w_items.wait()
+        w_theta.wait()
+        engine.update_items()

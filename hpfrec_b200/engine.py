@@ -155,6 +155,10 @@ class Engine:
     def sweep(self):
         _lib.check(self._lib.hpf_sweep(self._h))
 
+    def sweep_side(self, side):
+        """side 0: item-major pass (item-side partial sums), side 1: user-major pass."""
+        _lib.check(self._lib.hpf_sweep_side(self._h, int(side)))
+
     def update_users(self):
         _lib.check(self._lib.hpf_update_users(self._h))
 

@@ -93,6 +93,9 @@ int hpf_step_full(hpf_engine* h, int32_t niter);
  *   hpf_update_items     Lambda_shp/Lambda_rte/t_rte, identical on every shard
  * Device pointers: item_sums = (nI x ld) `real`; theta_colsum = k doubles. */
 int hpf_sweep(hpf_engine* h);
+/* One half of hpf_sweep: side 0 = item-major pass (fills item_sums, call it first so its all-reduce can
+ * overlap), side 1 = user-major pass. */
+int hpf_sweep_side(hpf_engine* h, int32_t side);
 int hpf_update_users(hpf_engine* h);
 int hpf_update_items(hpf_engine* h);
 int hpf_partials(hpf_engine* h, void** item_sums, int64_t* item_sums_count, void** theta_colsum,
