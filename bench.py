@@ -261,11 +261,17 @@ def run_ours(a):
     if world > 1:
         partial = hdist.engine_partial_tensors(eng, local)
 
+        mode = os.environ.get("HPF_MULTI", "peer")
+        if mode == "peer":
+            hdist.attach_peers(eng)
+
         def steps(n):
-            if os.environ.get("HPF_NO_OVERLAP"):
+            if mode == "plain":
                 hdist.run_sharded_iterations(eng, n, partial)
-            else:
+            elif mode == "overlap":
                 hdist.run_sharded_iterations_overlapped(eng, n, partial)
+            else:
+                hdist.run_sharded_iterations_peer(eng, n)
     else:
         def steps(n):
             eng.step_full(n)
@@ -342,7 +348,10 @@ def run_ours(a):
             e.set_hyper(0.3, 0.3, 1.0, 0.3, 0.3, 1.0)
             e.load_state(*hstate)
             e.load_coo(hu, hi_, hy)
-            if world > 1:
+            if world > 1 and os.environ.get("HPF_MULTI", "peer") == "peer":
+                hdist.attach_peers(e)
+                hdist.run_sharded_iterations_peer(e, a.steps)
+            elif world > 1:
                 hdist.run_sharded_iterations_overlapped(e, a.steps, hdist.engine_partial_tensors(e, local))
             else:
                 e.step_full(a.steps)
@@ -402,7 +411,8 @@ def run_ours(a):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
-            "config": {"workload": workload_name(a), "parallelism": "user-sharded x%d, item side replicated" % world,
+            "config": {"workload": workload_name(a), "parallelism": "user-sharded x%d, item side replicated%s" % (
+                           world, "" if world == 1 else ", exchange=" + os.environ.get("HPF_MULTI", "peer")),
                        "l2": "inputs larger than L2 (triples %.2f GB + factors %.2f GB per GPU)" % (
                            2 * 12 * nnz_local_max / 1e9, 4 * (nUl + nI) * ld * rb / 1e9),
                        "timing": "CUDA events on the engine stream, barrier+synchronize both sides, max over ranks",

@@ -33,6 +33,11 @@ SIGNATURES = {
     "hpf_update_users": ([_P], _c.c_int),
     "hpf_update_items": ([_P], _c.c_int),
     "hpf_partials": ([_P, _c.POINTER(_P), _c.POINTER(_I64), _c.POINTER(_P), _c.POINTER(_I64)], _c.c_int),
+    "hpf_peer_export": ([_P, _P], _c.c_int),
+    "hpf_peer_attach": ([_P, _I32, _I32, _P], _c.c_int),
+    "hpf_update_items_peer": ([_P, _I32], _c.c_int),
+    "hpf_peer_finish": ([_P], _c.c_int),
+    "hpf_beta_colsum": ([_P, _c.POINTER(_P), _c.POINTER(_I64)], _c.c_int),
     "hpf_step_batch": ([_P, _P, _P, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _D, _D, _I32], _c.c_int),
     "hpf_llk": ([_P, _P, _P, _P, _I64, _I32, _I32, _c.POINTER(_D)], _c.c_int),
     "hpf_llk_train": ([_P, _I32, _c.POINTER(_D)], _c.c_int),

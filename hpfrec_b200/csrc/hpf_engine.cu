@@ -119,6 +119,10 @@ struct hpf_engine {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     double phase_ms[4] = {0, 0, 0, 0};
     int64_t phase_iters = 0;
+    // multi-GPU peer memory (hpf_peer_attach): every rank's item-side buffers, opened through CUDA IPC
+    hpf::PeerTable peers;
+    bool peer_attached = false;
+    std::vector<void*> ipc_opened;
     // minibatch membership stamps (allocated at the first hpf_step_batch)
     int *stamp_u = nullptr, *stamp_i = nullptr;
     int batch_step = 0;
@@ -659,6 +663,8 @@ int hpf_destroy(hpf_engine* h) {
     free_data(h);
     for (auto e : h->ev)
         if (e) cudaEventDestroy(e);
+    for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+    h->ipc_opened.clear();
     void* ptrs[] = {h->Gshp, h->Grte, h->Lshp, h->Lrte, h->krte, h->trte, h->xu, h->xi, h->accU, h->accI, h->Tsum, h->Bsum, h->stamp_u, h->stamp_i};
     for (void* p : ptrs) cudaFree(p);
     delete h;
@@ -920,6 +926,94 @@ int hpf_step_full(hpf_engine* h, int32_t niter) {
         }
     }
     h->mat_valid = true;
+    return HPF_OK;
+}
+
+// ---- multi-GPU peer memory ----------------------------------------------------------------------------
+int hpf_peer_export(hpf_engine* h, void* handles) {
+    if (!h || !handles) return fail(HPF_EINVAL, "NULL argument");
+    DeviceGuard guard(h->device);
+    void* bufs[HPF_PEER_BUFFERS] = {h->accI, h->xi, h->trte, h->Lshp, h->Lrte};
+    for (int b = 0; b < HPF_PEER_BUFFERS; ++b)
+        CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)((char*)handles + (size_t)b * HPF_IPC_HANDLE_BYTES), bufs[b]));
+    return HPF_OK;
+}
+
+int hpf_peer_attach(hpf_engine* h, int32_t rank, int32_t world, const void* all_handles) {
+    if (!h || !all_handles) return fail(HPF_EINVAL, "NULL argument");
+    if (world < 1 || world > hpf::kMaxPeers || rank < 0 || rank >= world)
+        return fail(HPF_EINVAL, "bad rank/world (%d/%d, at most %d peers)", rank, world, hpf::kMaxPeers);
+    static_assert(sizeof(cudaIpcMemHandle_t) <= HPF_IPC_HANDLE_BYTES, "IPC handle larger than the ABI slot");
+    DeviceGuard guard(h->device);
+    for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+    h->ipc_opened.clear();
+    h->peer_attached = false;
+    void* own[HPF_PEER_BUFFERS] = {h->accI, h->xi, h->trte, h->Lshp, h->Lrte};
+    for (int p = 0; p < world; ++p) {
+        void* ptr[HPF_PEER_BUFFERS];
+        for (int b = 0; b < HPF_PEER_BUFFERS; ++b) {
+            if (p == rank) {
+                ptr[b] = own[b];
+                continue;
+            }
+            cudaIpcMemHandle_t hd;
+            memcpy(&hd, (const char*)all_handles + ((size_t)p * HPF_PEER_BUFFERS + b) * HPF_IPC_HANDLE_BYTES, sizeof(hd));
+            CK(cudaIpcOpenMemHandle(&ptr[b], hd, cudaIpcMemLazyEnablePeerAccess));
+            h->ipc_opened.push_back(ptr[b]);
+        }
+        h->peers.acc[p] = ptr[0];
+        h->peers.x[p] = ptr[1];
+        h->peers.rate[p] = ptr[2];
+        h->peers.shp[p] = ptr[3];
+        h->peers.rte[p] = ptr[4];
+    }
+    h->peers.world = world;
+    h->peers.rank = rank;
+    h->peer_attached = true;
+    return HPF_OK;
+}
+
+int hpf_update_items_peer(hpf_engine* h, int32_t materialize) {
+    if (!h) return fail(HPF_EINVAL, "engine is NULL");
+    if (!h->peer_attached) return fail(HPF_ESTATE, "hpf_peer_attach has not been called");
+    if (!h->x_valid) return fail(HPF_ESTATE, "hpf_update_items_peer must follow hpf_sweep");
+    DeviceGuard guard(h->device);
+    const int r0 = (int)(h->nI * (int64_t)h->peers.rank / h->peers.world);
+    const int r1 = (int)(h->nI * (int64_t)(h->peers.rank + 1) / h->peers.world);
+    CK(cudaMemsetAsync(h->Bsum, 0, sizeof(double) * h->ld, h->stream));
+    if (r1 > r0) {
+        TRY(dispatch(h->rb, h->ld, [&](auto cfg) {
+            using C = decltype(cfg);
+            using real = typename C::real;
+            const int grid = row_grid(r1 - r0, C::lpg);
+            const size_t smem = sizeof(double) * h->ld;
+            const real prior = (real)h->c, shp_rate = (real)h->t_shp, add_rate = (real)h->add_t;
+            if (materialize)
+                hpf::update_items_peer_kernel<real, C::lpg, C::vpl, true><<<grid, 256, smem, h->stream>>>(
+                    r0, r1, h->ld, h->k, h->peers, h->Tsum, h->Bsum, prior, shp_rate, add_rate);
+            else
+                hpf::update_items_peer_kernel<real, C::lpg, C::vpl, false><<<grid, 256, smem, h->stream>>>(
+                    r0, r1, h->ld, h->k, h->peers, h->Tsum, h->Bsum, prior, shp_rate, add_rate);
+            h->launches++;
+            CKK();
+            return HPF_OK;
+        }));
+    }
+    h->mat_valid = materialize != 0;
+    return HPF_OK;
+}
+
+int hpf_peer_finish(hpf_engine* h) {
+    if (!h) return fail(HPF_EINVAL, "engine is NULL");
+    DeviceGuard guard(h->device);
+    CK(cudaMemsetAsync(h->accI, 0, h->mat_bytes(h->nI), h->stream));
+    return HPF_OK;
+}
+
+int hpf_beta_colsum(hpf_engine* h, void** ptr, int64_t* count) {
+    if (!h || !ptr) return fail(HPF_EINVAL, "NULL argument");
+    *ptr = h->Bsum;
+    if (count) *count = h->k;
     return HPF_OK;
 }
 

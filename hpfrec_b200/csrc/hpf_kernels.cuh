@@ -332,6 +332,119 @@ update_rows_kernel(int nrows, int ld, int k, real* __restrict__ x, real* __restr
 }
 
 // =============================================================================================
+// Fused reduce-scatter + item update + all-gather over NVLink peer memory (multi-GPU).
+// Rank `rank` owns item rows [r0, r1).  For each owned row it (1) loads the row's partial sums from
+// EVERY rank's item_sums buffer (P2P LDG.128 over NVLink, fixed rank order => deterministic and the
+// same bits on every replica), (2) applies the item update of update_rows_kernel (pxi:255-259 + next
+// iteration's softmax factor), (3) stores the new factor row and rate (and, when MAT, shape/rate
+// matrices) into EVERY rank's replica (P2P STG.128).  Column sums of Beta over the owned rows are
+// accumulated locally (the caller all-reduces those k doubles, which is also the barrier that
+// publishes the peer writes).
+// =============================================================================================
+constexpr int kMaxPeers = 16;
+struct PeerTable {
+    void* acc[kMaxPeers];
+    void* x[kMaxPeers];
+    void* rate[kMaxPeers];
+    void* shp[kMaxPeers];
+    void* rte[kMaxPeers];
+    int world;
+    int rank;
+};
+
+template <typename real, int LPG, int VPL, bool MAT>
+__global__ void __launch_bounds__(256)
+update_items_peer_kernel(int r0, int r1, int ld, int k, PeerTable pt, const double* __restrict__ colsum_other,
+                         double* __restrict__ colsum_out, real prior, real shp_rate, real add_rate) {
+    constexpr int EPV = Pack<real>::N;
+    extern __shared__ double s_col[];
+    for (int j = threadIdx.x; j < ld; j += blockDim.x) s_col[j] = 0.0;
+    __syncthreads();
+    const int gl = (threadIdx.x & 31) % LPG;
+    const unsigned gmask = group_mask<LPG>();
+    const int groups_per_block = blockDim.x / LPG;
+    const int g0 = blockIdx.x * groups_per_block + threadIdx.x / LPG;
+    const int gstride = gridDim.x * groups_per_block;
+    const real* x_local = (const real*)pt.x[pt.rank];
+    const real* rate_local = (const real*)pt.rate[pt.rank];
+    int off[VPL];
+    bool act[VPL];
+    real other[VPL][EPV], csum[VPL][EPV];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        off[v] = (gl + LPG * v) * EPV;
+        act[v] = off[v] < ld;
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) {
+            const int j = off[v] + e;
+            other[v][e] = (act[v] && j < k) ? (real)colsum_other[j] : real(0);
+            csum[v][e] = real(0);
+        }
+    }
+    for (int r = r0 + g0; r < r1; r += gstride) {
+        const real inv = shp_rate / rate_local[r];
+        Pack<real> shp[VPL], rte[VPL], E[VPL];
+        real rowsum = real(0);
+        real m = -INFINITY;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            if (!act[v]) continue;
+            const size_t at = (size_t)r * ld + off[v];
+            Pack<real> av = pack_zero<real>();
+            for (int p = 0; p < pt.world; ++p) {
+                const Pack<real> pv = ld_pack((const real*)pt.acc[p] + at);
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) av.v[e] += pv.v[e];
+            }
+            const Pack<real> xv = ld_pack(x_local + at);
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) {
+                const bool real_col = off[v] + e < k;
+                const real s_ = fma(xv.v[e], av.v[e], prior);
+                const real t_ = inv + other[v][e];
+                shp[v].v[e] = real_col ? s_ : real(0);
+                rte[v].v[e] = real_col ? t_ : real(1);
+                const real th = real_col ? rratio(s_, t_) : real(0);
+                rowsum += th;
+                csum[v][e] += th;
+                const real lg = real_col ? elog(s_, t_) : -INFINITY;
+                E[v].v[e] = lg;
+                m = lg > m ? lg : m;
+            }
+        }
+        rowsum = group_sum<LPG>(rowsum, gmask);
+        m = group_max<LPG>(m, gmask);
+        const real new_rate = add_rate + rowsum;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            if (!act[v]) continue;
+            const size_t at = (size_t)r * ld + off[v];
+            Pack<real> xn;
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) xn.v[e] = (off[v] + e < k) ? rexp(E[v].v[e] - m) : real(0);
+            for (int p = 0; p < pt.world; ++p) {
+                st_pack((real*)pt.x[p] + at, xn);
+                if (MAT) {
+                    st_pack((real*)pt.shp[p] + at, shp[v]);
+                    st_pack((real*)pt.rte[p] + at, rte[v]);
+                }
+            }
+        }
+        if (gl == 0)
+            for (int p = 0; p < pt.world; ++p) ((real*)pt.rate[p])[r] = new_rate;
+    }
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        if (!act[v]) continue;
+#pragma unroll
+        for (int e = 0; e < EPV; ++e)
+            if (off[v] + e < k) atomicAdd(&s_col[off[v] + e], (double)csum[v][e]);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < k; j += blockDim.x) atomicAdd(colsum_out + j, s_col[j]);
+}
+
+// =============================================================================================
 // K1 alone: x rows from materialised (shp, rte); optional row list (minibatch) and optional column
 // sums of shp/rte (used to seed Beta.sum(axis=0) after a state upload).
 // =============================================================================================

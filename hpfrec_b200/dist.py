@@ -100,3 +100,38 @@ def run_sharded_iterations_overlapped(engine, niter, partial_tensors=None, group
         w_items.wait()
         w_theta.wait()
         engine.update_items()
+
+
+def attach_peers(engine, group=None):
+    """Exchanges the CUDA-IPC handles of every rank's item-side buffers (all-gather over the process
+    group) and maps them into `engine`, enabling run_sharded_iterations_peer."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    mine = torch.frombuffer(bytearray(engine.peer_export()), dtype=torch.uint8).cuda()
+    allh = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allh, mine, group=group)
+    engine.peer_attach(rank, world, b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh))
+
+
+def run_sharded_iterations_peer(engine, niter, group=None, materialize_last=True):
+    """User-sharded iterations with the item-side exchange fused into ONE kernel over NVLink peer
+    memory (hpf_update_items_peer): each rank reduces its slice of item rows straight out of the other
+    ranks' partial-sum buffers, updates it, and stores the result into every replica.  The only NCCL
+    traffic left is two k-double all-reduces per iteration (Theta and Beta column sums), which double
+    as the two cross-GPU barriers the kernel needs."""
+    import torch
+    import torch.distributed as dist
+    dev = torch.cuda.current_device()
+    _, _, p_theta, n_theta = engine.partials()
+    p_beta, n_beta = engine.beta_colsum()
+    t_theta = wrap_device_buffer(p_theta, n_theta, torch.float64, dev)
+    t_beta = wrap_device_buffer(p_beta, n_beta, torch.float64, dev)
+    for it in range(int(niter)):
+        engine.sweep_side(0)
+        engine.sweep_side(1)
+        engine.update_users()
+        dist.all_reduce(t_theta, op=dist.ReduceOp.SUM, group=group)
+        engine.update_items_peer(materialize_last and it == niter - 1)
+        dist.all_reduce(t_beta, op=dist.ReduceOp.SUM, group=group)
+        engine.peer_finish()

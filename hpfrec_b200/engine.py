@@ -172,6 +172,32 @@ class Engine:
                                           ctypes.byref(n2)))
         return p1.value, n1.value, p2.value, n2.value
 
+    # -- NVLink peer memory (one process per GPU) --------------------------------------------------
+    PEER_HANDLE_BYTES = 64 * 5
+
+    def peer_export(self):
+        buf = ctypes.create_string_buffer(self.PEER_HANDLE_BYTES)
+        _lib.check(self._lib.hpf_peer_export(self._h, ctypes.cast(buf, ctypes.c_void_p)))
+        return bytes(buf.raw)
+
+    def peer_attach(self, rank, world, all_handles):
+        """all_handles: the concatenation, in rank order, of every rank's peer_export() bytes."""
+        if len(all_handles) != world * self.PEER_HANDLE_BYTES:
+            raise ValueError("expected %d bytes of IPC handles" % (world * self.PEER_HANDLE_BYTES))
+        buf = ctypes.create_string_buffer(bytes(all_handles), len(all_handles))
+        _lib.check(self._lib.hpf_peer_attach(self._h, int(rank), int(world), ctypes.cast(buf, ctypes.c_void_p)))
+
+    def update_items_peer(self, materialize=True):
+        _lib.check(self._lib.hpf_update_items_peer(self._h, int(bool(materialize))))
+
+    def peer_finish(self):
+        _lib.check(self._lib.hpf_peer_finish(self._h))
+
+    def beta_colsum(self):
+        p, n = ctypes.c_void_p(), ctypes.c_int64()
+        _lib.check(self._lib.hpf_beta_colsum(self._h, ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value
+
     # -- minibatch ----------------------------------------------------------------------------------
     def step_batch(self, ix_u, ix_i, Y, users, items, user_batch, rho, mult, blend_all_rates):
         ib = _index_bytes(ix_u)

@@ -101,6 +101,25 @@ int hpf_update_items(hpf_engine* h);
 int hpf_partials(hpf_engine* h, void** item_sums, int64_t* item_sums_count, void** theta_colsum,
                  int64_t* theta_colsum_count);
 
+/* Fused alternative to <all-reduce item_sums> + hpf_update_items for one box with NVLink peer access
+ * (one process per GPU).  Setup once: every rank calls hpf_peer_export (HPF_PEER_BUFFERS CUDA-IPC
+ * handles of HPF_IPC_HANDLE_BYTES each: item_sums, item softmax factors, t_rte, Lambda_shp,
+ * Lambda_rte), the caller all-gathers them rank-major and passes the table to hpf_peer_attach.
+ * Per iteration, after hpf_sweep + hpf_update_users:
+ *   <all-reduce theta_colsum>      (k doubles; also the barrier that makes every rank's item_sums final)
+ *   hpf_update_items_peer          ONE kernel: each rank sums ITS slice of item rows over all ranks'
+ *                                  item_sums (P2P loads), updates them, stores the results into every
+ *                                  rank's replica (P2P stores); materialize != 0 also stores shp/rte
+ *   <all-reduce beta_colsum>       (hpf_beta_colsum, k doubles; the barrier that publishes the stores)
+ *   hpf_peer_finish                re-zeroes the local item_sums */
+#define HPF_IPC_HANDLE_BYTES 64
+#define HPF_PEER_BUFFERS 5
+int hpf_peer_export(hpf_engine* h, void* handles);
+int hpf_peer_attach(hpf_engine* h, int32_t rank, int32_t world, const void* all_handles);
+int hpf_update_items_peer(hpf_engine* h, int32_t materialize);
+int hpf_peer_finish(hpf_engine* h);
+int hpf_beta_colsum(hpf_engine* h, void** ptr, int64_t* count);
+
 /* ---- minibatch step (replaces Cython partial_fit pxi:423-473 and the SVI epoch bodies
  *      pxi:275-325 / 329-377) -------------------------------------------------------------- */
 

@@ -32,7 +32,8 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     ok = True
     for dtype, rb, tol, overlapped in ((np.float64, 8, 1e-10, True), (np.float64, 8, 1e-10, False),
-                                       (np.float32, 4, 2e-4, True)):
+                                       (np.float64, 8, 1e-10, "peer"), (np.float32, 4, 2e-4, True),
+                                       (np.float32, 4, 2e-4, "peer")):
         nU, nI, nnz, k, its = 60000, 25000, 1_500_000, 50, 6
         u, i, y = bench.synth_coo_torch(nU, nI, nnz, dev, seed=7)
         y = y.to(torch.float64 if rb == 8 else torch.float32)
@@ -46,7 +47,10 @@ def main():
         eng.load_state(np.ascontiguousarray(Gs[lo:hi]), np.ascontiguousarray(Gr[lo:hi]), Ls, Lr,
                        np.ascontiguousarray(kr[lo:hi]), tr)
         eng.load_coo(lu, li, ly)
-        if overlapped:
+        if overlapped == "peer":
+            hdist.attach_peers(eng)
+            hdist.run_sharded_iterations_peer(eng, its)
+        elif overlapped:
             hdist.run_sharded_iterations_overlapped(eng, its)
         else:
             hdist.run_sharded_iterations(eng, its)
