@@ -383,19 +383,35 @@ update_items_peer_kernel(int r0, int r1, int ld, int k, PeerTable pt, const doub
     }
     for (int r = r0 + g0; r < r1; r += gstride) {
         const real inv = shp_rate / rate_local[r];
-        Pack<real> shp[VPL], rte[VPL], E[VPL];
+        Pack<real> shp[VPL], rte[VPL], E[VPL], asum[VPL];
         real rowsum = real(0);
         real m = -INFINITY;
+        // all peer loads of a batch of 8 ranks are issued before the first add: NVLink reads have
+        // ~2 us latency, so memory-level parallelism per thread is what fills the links
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) asum[v] = pack_zero<real>();
+        for (int p0 = 0; p0 < pt.world; p0 += 8) {
+            Pack<real> pv[VPL][8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const bool have = p0 + q < pt.world;
+                const real* base = (const real*)pt.acc[have ? p0 + q : pt.rank];
+#pragma unroll
+                for (int v = 0; v < VPL; ++v)
+                    pv[v][q] = (have && act[v]) ? ld_pack(base + (size_t)r * ld + off[v]) : pack_zero<real>();
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)  // fixed rank order: every replica receives identical bits
+#pragma unroll
+                for (int v = 0; v < VPL; ++v)
+#pragma unroll
+                    for (int e = 0; e < EPV; ++e) asum[v].v[e] += pv[v][q].v[e];
+        }
 #pragma unroll
         for (int v = 0; v < VPL; ++v) {
             if (!act[v]) continue;
             const size_t at = (size_t)r * ld + off[v];
-            Pack<real> av = pack_zero<real>();
-            for (int p = 0; p < pt.world; ++p) {
-                const Pack<real> pv = ld_pack((const real*)pt.acc[p] + at);
-#pragma unroll
-                for (int e = 0; e < EPV; ++e) av.v[e] += pv.v[e];
-            }
+            const Pack<real> av = asum[v];
             const Pack<real> xv = ld_pack(x_local + at);
 #pragma unroll
             for (int e = 0; e < EPV; ++e) {
