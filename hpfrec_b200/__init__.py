@@ -726,8 +726,8 @@ class HPF:
             raise Exception("Can only exclude seen items when passing 'keep_data=True' to .fit")
 
         def seen_by_user():
-            st = self._st_ix_user[user]
-            return self.seen[st: st + self._n_seen_by_user[user]]
+            st = int(self._st_ix_user[user])      # may be an unsigned 64-bit scalar after an SVI fit
+            return self.seen[st: st + int(self._n_seen_by_user[user])]
 
         def back(rows):
             return self.item_mapping_[rows] if self.reindex else rows

@@ -39,6 +39,7 @@ SIGNATURES = {
     "hpf_peer_finish": ([_P], _c.c_int),
     "hpf_beta_colsum": ([_P, _c.POINTER(_P), _c.POINTER(_I64)], _c.c_int),
     "hpf_step_batch": ([_P, _P, _P, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _D, _D, _I32], _c.c_int),
+    "hpf_step_batch_ids": ([_P, _P, _I64, _I32, _I32, _D, _D, _I32], _c.c_int),
     "hpf_llk": ([_P, _P, _P, _P, _I64, _I32, _I32, _c.POINTER(_D)], _c.c_int),
     "hpf_llk_train": ([_P, _I32, _c.POINTER(_D)], _c.c_int),
     "hpf_predict": ([_P, _P, _P, _I64, _I32, _P], _c.c_int),

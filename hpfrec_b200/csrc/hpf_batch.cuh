@@ -73,7 +73,10 @@ batch_prepare_kernel(int nrows, const int* __restrict__ rows, int ld, int k, con
         act[v] = off[v] < ld;
     }
     for (int q = g0; q < nrows; q += gstride) {
-        const int r = rows[q];
+        // rows == nullptr: walk ALL rows and prepare those already stamped for this step (the unique
+        // opposite-side ids of a device-assembled batch, see batch_expand_kernel)
+        const int r = rows ? rows[q] : q;
+        if (!rows && stamp[r] != step) continue;  // uniform inside the lane group
         Pack<real> E[VPL];
         real m = -INFINITY;
 #pragma unroll
@@ -98,7 +101,7 @@ batch_prepare_kernel(int nrows, const int* __restrict__ rows, int ld, int k, con
             st_pack(x + (size_t)r * ld + off[v], xn);
             st_pack(acc + (size_t)r * ld + off[v], pack_zero<real>());
         }
-        if (gl == 0) stamp[r] = step;
+        if (rows && gl == 0) stamp[r] = step;
     }
 }
 
@@ -195,7 +198,7 @@ batch_minor_kernel(int nrows, const int* __restrict__ rows, int ld, int k, const
                    const real* __restrict__ acc, real* __restrict__ shp, real* __restrict__ rte,
                    real* __restrict__ rate, const int* __restrict__ stamp, int step,
                    const double* __restrict__ colsum_major, real prior, real shp_rate, real add_rate,
-                   real rho, real mult) {
+                   real rho, real mult, int blend_all) {
     constexpr int EPV = Pack<real>::N;
     const int gl = (threadIdx.x & 31) % LPG;
     const unsigned gmask = group_mask<LPG>();
@@ -218,6 +221,7 @@ batch_minor_kernel(int nrows, const int* __restrict__ rows, int ld, int k, const
     for (int q = g0; q < nrows; q += gstride) {
         const int r = rows ? rows[q] : q;
         const bool inb = rows ? true : (stamp[r] == step);
+        if (!inb && !blend_all) continue;  // all-rows walk of an SVI step: only stamped rows change
         const real old_rate = rate[r];
         const real inv = shp_rate / old_rate;
         real rowsum = real(0);
@@ -246,6 +250,49 @@ batch_minor_kernel(int nrows, const int* __restrict__ rows, int ld, int k, const
         rowsum = group_sum<LPG>(rowsum, gmask);
         if (gl == 0) rate[r] = rho * (add_rate + rowsum) + prev * old_rate;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5  device-side minibatch assembly (replaces get_i_batch_pass1/2 + np.unique, pxi:27-42, 774-797):
+//   count:   cnt[q] = ptr[ids[q]+1] - ptr[ids[q]]            (then an exclusive scan gives off[])
+//   expand:  for every nnz of every listed row, copy the triple into compact (major, minor, y) arrays
+//            in row-after-row order and stamp the minor id as a member of this step's batch
+// ---------------------------------------------------------------------------------------------
+__global__ void batch_count_kernel(int n_ids, const int* __restrict__ ids, const int* __restrict__ ptr,
+                                   int* __restrict__ cnt) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n_ids) cnt[q] = ptr[ids[q] + 1] - ptr[ids[q]];
+}
+
+template <typename real>
+__global__ void __launch_bounds__(256)
+batch_expand_kernel(int n_ids, const int* __restrict__ ids, const int* __restrict__ ptr,
+                    const int* __restrict__ off, const int* __restrict__ src_minor,
+                    const real* __restrict__ src_val, int* __restrict__ out_major, int* __restrict__ out_minor,
+                    real* __restrict__ out_val, int* __restrict__ stamp_minor, int step) {
+    // one warp per listed row: coalesced copy of its CSR/CSC segment
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int q = warp; q < n_ids; q += nwarps) {
+        const int id = ids[q];
+        const int beg = ptr[id], len = ptr[id + 1] - beg, dst = off[q];
+        for (int t = lane; t < len; t += 32) {
+            const int m = src_minor[beg + t];
+            out_major[dst + t] = id;
+            out_minor[dst + t] = m;
+            out_val[dst + t] = src_val[beg + t];
+            stamp_minor[m] = step;  // benign race: every writer stores the same value
+        }
+    }
+}
+
+// row pointer array of a sorted ordering: ptr[r] = first position with row >= r
+__global__ void row_ptr_kernel(const int* __restrict__ row, long long nnz, int nrows, int* __restrict__ ptr) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > nnz) return;
+    const int cur = i < nnz ? row[i] : nrows;
+    const int prv = i > 0 ? row[i - 1] : -1;
+    for (int r = prv + 1; r <= cur; ++r) ptr[r] = (int)i;
 }
 
 }  // namespace hpf

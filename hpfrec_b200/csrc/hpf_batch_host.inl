@@ -1,6 +1,110 @@
-// hpf_step_batch: one minibatch update (included at the end of hpf_engine.cu; same translation unit).
+// Minibatch steps (included at the end of hpf_engine.cu; same translation unit).
 // Mirrors hpfrec/cython_loops.pxi 275-325 (user epoch body), 329-377 (item epoch body) and
-// 423-473 (Cython partial_fit).
+// 423-473 (Cython partial_fit).  Two front ends share one core:
+//   hpf_step_batch      explicit COO triples + unique id lists from the caller (partial_fit)
+//   hpf_step_batch_ids  only the batched row ids; the triples come from the resident CSR/CSC
+//                       orderings (SVI epochs of fit_hpf; replaces get_unique_items_batch pxi:27-42)
+
+namespace {
+
+int ensure_stamps(hpf_engine* h) {
+    if (h->stamp_u) return HPF_OK;
+    CK(cudaMalloc(&h->stamp_u, sizeof(int) * (size_t)(h->nU > 0 ? h->nU : 1)));
+    CK(cudaMalloc(&h->stamp_i, sizeof(int) * (size_t)(h->nI > 0 ? h->nI : 1)));
+    CK(cudaMemsetAsync(h->stamp_u, 0, sizeof(int) * (size_t)(h->nU > 0 ? h->nU : 1), h->stream));
+    CK(cudaMemsetAsync(h->stamp_i, 0, sizeof(int) * (size_t)(h->nI > 0 ? h->nI : 1), h->stream));
+    h->batch_step = 0;
+    return HPF_OK;
+}
+
+// Core of one minibatch update.  iu/ii/yv: device triples of the batch (int32 ids).  list_major: the
+// batched ids (device int32).  list_minor: unique opposite-side ids, or nullptr when they are already
+// stamped for `step` (device-assembled batches).  The minor side is walked by list when one is
+// given and rates are blended on batch rows only; otherwise all rows are walked under the stamp.
+int batch_core(hpf_engine* h, const int* iu, const int* ii, const void* yv, int64_t nnz, const int* list_major,
+               int64_t n_major_ids, const int* list_minor, int64_t n_minor_ids, bool user_batch, double rho,
+               double mult, bool blend_all, int step) {
+    h->x_valid = false;  // per-row factors / accumulators are only valid for the batch rows from here on
+    drop_graphs(h);
+    return dispatch(h->rb, h->ld, [&](auto cfg) {
+        using C = decltype(cfg);
+        using real = typename C::real;
+        const int ld = h->ld, k = h->k;
+        const size_t smem = sizeof(double) * ld;
+        const bool ub = user_batch;
+        const int64_t nM = ub ? h->nU : h->nI, nm = ub ? h->nI : h->nU;
+        real *shpM = (real*)(ub ? h->Gshp : h->Lshp), *rteM = (real*)(ub ? h->Grte : h->Lrte);
+        real *shpm = (real*)(ub ? h->Lshp : h->Gshp), *rtem = (real*)(ub ? h->Lrte : h->Grte);
+        real *xM = (real*)(ub ? h->xu : h->xi), *xm = (real*)(ub ? h->xi : h->xu);
+        real *accM = (real*)(ub ? h->accU : h->accI), *accm = (real*)(ub ? h->accI : h->accU);
+        real *rateM = (real*)(ub ? h->krte : h->trte), *ratem = (real*)(ub ? h->trte : h->krte);
+        int *stampM = ub ? h->stamp_u : h->stamp_i, *stampm = ub ? h->stamp_i : h->stamp_u;
+        double *csM = ub ? h->Tsum : h->Bsum, *csm = ub ? h->Bsum : h->Tsum;
+        const real priorM = (real)(ub ? h->a : h->c), priorm = (real)(ub ? h->c : h->a);
+        const real k_shp = (real)h->k_shp, t_shp = (real)h->t_shp;
+        const real add_k = (real)h->add_k, add_t = (real)h->add_t;
+        const real srM = ub ? k_shp : t_shp, srm = ub ? t_shp : k_shp;
+        const real addM = ub ? add_k : add_t, addm = ub ? add_t : add_k;
+
+        // 1. softmax factors of the participating rows from the current state; zero their sums
+        if (n_major_ids > 0) {
+            hpf::batch_prepare_kernel<real, C::lpg, C::vpl><<<row_grid(n_major_ids, C::lpg), 256, 0, h->stream>>>(
+                (int)n_major_ids, list_major, ld, k, shpM, rteM, xM, accM, stampM, step);
+            h->launches++;
+        }
+        const int64_t n_prep_minor = list_minor ? n_minor_ids : nm;
+        if (n_prep_minor > 0) {
+            hpf::batch_prepare_kernel<real, C::lpg, C::vpl><<<row_grid(n_prep_minor, C::lpg), 256, 0, h->stream>>>(
+                (int)n_prep_minor, list_minor, ld, k, shpm, rtem, xm, accm, stampm, step);
+            h->launches++;
+        }
+        CKK();
+        // 2. phi + scatter over the batch triples (update_phi + update_G_n_L_sh)
+        TRY(launch_sweep_coo<C>(h, iu, ii, yv, nnz, h->xu, h->xi, h->accU, h->accI, ld, nullptr, k, h->stream));
+        // 3. column sums of the minor side's current expectation (Beta.sum(0) at pxi:300, Theta.sum(0) at 352)
+        CK(cudaMemsetAsync(csm, 0, sizeof(double) * ld, h->stream));
+        CK(cudaMemsetAsync(csM, 0, sizeof(double) * ld, h->stream));
+        if (nm > 0) {
+            long long want = (nm * (long long)ld + 255) / 256;
+            if (want > 148 * 8) want = 148 * 8;
+            hpf::colsum_kernel<real><<<(unsigned)want, 256, smem, h->stream>>>(nm, ld, k, shpm, rtem, csm);
+            h->launches++;
+            CKK();
+        }
+        // 4. major side, all rows
+        if (nM > 0) {
+            hpf::batch_major_kernel<real, C::lpg, C::vpl><<<row_grid(nM, C::lpg), 256, smem, h->stream>>>(
+                (int)nM, ld, k, xM, accM, shpM, rteM, rateM, stampM, step, csm, csM, priorM, srM, addM, (real)rho,
+                blend_all ? 1 : 0);
+            h->launches++;
+            CKK();
+        }
+        // 5. minor side: the listed rows (SVI with a caller list), or all rows under the stamp
+        const bool walk_all = blend_all || list_minor == nullptr;
+        const int64_t nrows5 = walk_all ? nm : n_minor_ids;
+        if (nrows5 > 0) {
+            hpf::batch_minor_kernel<real, C::lpg, C::vpl><<<row_grid(nrows5, C::lpg), 256, 0, h->stream>>>(
+                (int)nrows5, walk_all ? nullptr : list_minor, ld, k, xm, accm, shpm, rtem, ratem, stampm, step, csM,
+                priorm, srm, addm, (real)rho, (real)mult, blend_all ? 1 : 0);
+            h->launches++;
+            CKK();
+        }
+        return HPF_OK;
+    });
+}
+
+// grow-only device scratch
+int grow_bytes(void** p, int64_t* cap_elems, int64_t need_elems, size_t elem) {
+    if (*p != nullptr && need_elems <= *cap_elems) return HPF_OK;
+    cudaFree(*p);
+    *p = nullptr;
+    const int64_t n = need_elems + need_elems / 4 + 16;
+    CK(cudaMalloc(p, (size_t)n * elem));
+    *cap_elems = n;
+    return HPF_OK;
+}
+
+}  // namespace
 
 extern "C" int hpf_step_batch(hpf_engine* h, const void* ix_u, const void* ix_i, const void* Y, int64_t nnz,
                               const void* users, int64_t n_users, const void* items, int64_t n_items,
@@ -14,14 +118,7 @@ extern "C" int hpf_step_batch(hpf_engine* h, const void* ix_u, const void* ix_i,
     if ((n_users > 0 && !users) || (n_items > 0 && !items)) return fail(HPF_EINVAL, "NULL id list");
     if (!(rho >= 0.0 && rho <= 1.0)) return fail(HPF_EINVAL, "step size must be in [0, 1]");
     DeviceGuard guard(h->device);
-    if (!h->stamp_u) {
-        CK(cudaMalloc(&h->stamp_u, sizeof(int) * (size_t)(h->nU > 0 ? h->nU : 1)));
-        CK(cudaMalloc(&h->stamp_i, sizeof(int) * (size_t)(h->nI > 0 ? h->nI : 1)));
-        CK(cudaMemsetAsync(h->stamp_u, 0, sizeof(int) * (size_t)(h->nU > 0 ? h->nU : 1), h->stream));
-        CK(cudaMemsetAsync(h->stamp_i, 0, sizeof(int) * (size_t)(h->nI > 0 ? h->nI : 1), h->stream));
-        h->batch_step = 0;
-    }
-    hpf_engine* sc = h;
+    TRY(ensure_stamps(h));
     h->batch_step += 1;
     const int step = h->batch_step;
 
@@ -51,74 +148,9 @@ extern "C" int hpf_step_batch(hpf_engine* h, const void* ix_u, const void* ix_i,
         if (bad) rc = fail(HPF_EINVAL, "index out of range in minibatch");
     }
     if (rc == HPF_OK) {
-        h->x_valid = false;  // per-row factors / accumulators are only valid for the batch rows from here on
-        drop_graphs(h);
-        rc = dispatch(h->rb, h->ld, [&](auto cfg) {
-            using C = decltype(cfg);
-            using real = typename C::real;
-            const int ld = h->ld, k = h->k;
-            const size_t smem = sizeof(double) * ld;
-            // roles
-            const bool ub = user_batch != 0;
-            const int64_t nM = ub ? h->nU : h->nI, nm = ub ? h->nI : h->nU;
-            real *shpM = (real*)(ub ? h->Gshp : h->Lshp), *rteM = (real*)(ub ? h->Grte : h->Lrte);
-            real *shpm = (real*)(ub ? h->Lshp : h->Gshp), *rtem = (real*)(ub ? h->Lrte : h->Grte);
-            real *xM = (real*)(ub ? h->xu : h->xi), *xm = (real*)(ub ? h->xi : h->xu);
-            real *accM = (real*)(ub ? h->accU : h->accI), *accm = (real*)(ub ? h->accI : h->accU);
-            real *rateM = (real*)(ub ? h->krte : h->trte), *ratem = (real*)(ub ? h->trte : h->krte);
-            int *stampM = ub ? sc->stamp_u : sc->stamp_i, *stampm = ub ? sc->stamp_i : sc->stamp_u;
-            const int *listM = ub ? ulist : ilist, *listm = ub ? ilist : ulist;
-            const int64_t nlM = ub ? n_users : n_items, nlm = ub ? n_items : n_users;
-            double *csM = ub ? h->Tsum : h->Bsum, *csm = ub ? h->Bsum : h->Tsum;
-            const real priorM = (real)(ub ? h->a : h->c), priorm = (real)(ub ? h->c : h->a);
-            const real k_shp = (real)h->k_shp, t_shp = (real)h->t_shp;
-            const real add_k = (real)h->add_k, add_t = (real)h->add_t;
-            const real srM = ub ? k_shp : t_shp, srm = ub ? t_shp : k_shp;
-            const real addM = ub ? add_k : add_t, addm = ub ? add_t : add_k;
-
-            // 1. softmax factors of the participating rows from the current state; zero their sums
-            if (nlM > 0) {
-                hpf::batch_prepare_kernel<real, C::lpg, C::vpl><<<row_grid(nlM, C::lpg), 256, 0, h->stream>>>(
-                    (int)nlM, listM, ld, k, shpM, rteM, xM, accM, stampM, step);
-                h->launches++;
-            }
-            if (nlm > 0) {
-                hpf::batch_prepare_kernel<real, C::lpg, C::vpl><<<row_grid(nlm, C::lpg), 256, 0, h->stream>>>(
-                    (int)nlm, listm, ld, k, shpm, rtem, xm, accm, stampm, step);
-                h->launches++;
-            }
-            CKK();
-            // 2. phi + scatter over the batch triples (update_phi + update_G_n_L_sh)
-            TRY(launch_sweep_coo<C>(h, u32, i32, yv, nnz, h->xu, h->xi, h->accU, h->accI, ld, nullptr, k, h->stream));
-            // 3. column sums of the minor side's current expectation (Beta.sum(0) at pxi:300, Theta.sum(0) at 352)
-            CK(cudaMemsetAsync(csm, 0, sizeof(double) * ld, h->stream));
-            CK(cudaMemsetAsync(csM, 0, sizeof(double) * ld, h->stream));
-            if (nm > 0) {
-                long long want = (nm * (long long)ld + 255) / 256;
-                if (want > 148 * 8) want = 148 * 8;
-                hpf::colsum_kernel<real><<<(unsigned)want, 256, smem, h->stream>>>(nm, ld, k, shpm, rtem, csm);
-                h->launches++;
-                CKK();
-            }
-            // 4. major side, all rows
-            if (nM > 0) {
-                hpf::batch_major_kernel<real, C::lpg, C::vpl><<<row_grid(nM, C::lpg), 256, smem, h->stream>>>(
-                    (int)nM, ld, k, xM, accM, shpM, rteM, rateM, stampM, step, csm, csM, priorM, srM, addM,
-                    (real)rho, blend_all_rates);
-                h->launches++;
-                CKK();
-            }
-            // 5. minor side: batch rows (SVI) or all rows (partial_fit)
-            const int64_t nrows5 = blend_all_rates ? nm : nlm;
-            if (nrows5 > 0) {
-                hpf::batch_minor_kernel<real, C::lpg, C::vpl><<<row_grid(nrows5, C::lpg), 256, 0, h->stream>>>(
-                    (int)nrows5, blend_all_rates ? nullptr : listm, ld, k, xm, accm, shpm, rtem, ratem, stampm, step,
-                    csM, priorm, srm, addm, (real)rho, (real)mult);
-                h->launches++;
-                CKK();
-            }
-            return HPF_OK;
-        });
+        const bool ub = user_batch != 0;
+        rc = batch_core(h, u32, i32, yv, nnz, ub ? ulist : ilist, ub ? n_users : n_items, ub ? ilist : ulist,
+                        ub ? n_items : n_users, ub, rho, mult, blend_all_rates != 0, step);
     }
     cudaError_t e = cudaStreamSynchronize(h->stream);
     if (rc == HPF_OK && e != cudaSuccess) rc = fail(HPF_ECUDA, "minibatch kernels failed: %s", cudaGetErrorString(e));
@@ -129,4 +161,99 @@ extern "C" int hpf_step_batch(hpf_engine* h, const void* ix_u, const void* ix_i,
     cudaFree(d_bad);
     cudaFree(yfree);
     return rc;
+}
+
+extern "C" int hpf_step_batch_ids(hpf_engine* h, const void* ids, int64_t n_ids, int32_t index_bytes,
+                                  int32_t user_batch, double rho, double mult, int32_t blend_all_rates) {
+    if (!h) return fail(HPF_EINVAL, "engine is NULL");
+    if (!h->state_loaded || !h->mat_valid) return fail(HPF_ESTATE, "no state loaded (call hpf_load_state first)");
+    if (!h->data_loaded || !h->A_ptr || !h->B_ptr)
+        return fail(HPF_ESTATE, "hpf_step_batch_ids needs triples loaded with a single L2 panel per side "
+                                "(set option panel_mb large enough before hpf_load_coo)");
+    if (n_ids < 0 || n_ids >= (1ll << 31)) return fail(HPF_EINVAL, "bad n_ids");
+    if (index_bytes != 4 && index_bytes != 8) return fail(HPF_EINVAL, "index_bytes must be 4 or 8");
+    if (n_ids > 0 && !ids) return fail(HPF_EINVAL, "NULL id list");
+    if (!(rho >= 0.0 && rho <= 1.0)) return fail(HPF_EINVAL, "step size must be in [0, 1]");
+    DeviceGuard guard(h->device);
+    TRY(ensure_stamps(h));
+    h->batch_step += 1;
+    const int step = h->batch_step;
+    const bool ub = user_batch != 0;
+    const int64_t n_major = ub ? h->nU : h->nI;
+    const int* ptr = ub ? h->A_ptr : h->B_ptr;
+    const int* src_minor = ub ? h->A_col : h->B_col;
+    const void* src_val = ub ? h->A_val : h->B_val;
+    int* stamp_minor = ub ? h->stamp_i : h->stamp_u;
+
+    // ids -> device int32, per-row counts, exclusive scan, total
+    if (n_ids + 1 > h->bt_cap_ids || !h->bt_ids) {
+        int64_t c1 = 0, c2 = 0, c3 = 0;
+        TRY(grow_bytes((void**)&h->bt_ids, &c1, n_ids + 1, sizeof(int)));
+        TRY(grow_bytes((void**)&h->bt_cnt, &c2, n_ids + 1, sizeof(int)));
+        TRY(grow_bytes((void**)&h->bt_off, &c3, n_ids + 1, sizeof(int)));
+        h->bt_cap_ids = c1;
+    }
+    int* d_bad = nullptr;
+    CK(cudaMalloc(&d_bad, 4));
+    cudaMemsetAsync(d_bad, 0, 4, h->stream);
+    int rc = stage_index(h, ids, n_ids, index_bytes, n_major, h->bt_ids, d_bad);
+    int total = 0;
+    if (rc == HPF_OK && n_ids > 0) {
+        int bad = 0;
+        cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, h->stream);
+        cudaStreamSynchronize(h->stream);
+        if (bad) rc = fail(HPF_EINVAL, "batch id out of range");
+    }
+    if (rc == HPF_OK && n_ids > 0) {
+        cudaMemsetAsync(h->bt_cnt + n_ids, 0, sizeof(int), h->stream);
+        hpf::batch_count_kernel<<<nblk(n_ids), 256, 0, h->stream>>>((int)n_ids, h->bt_ids, ptr, h->bt_cnt);
+        h->launches++;
+        size_t need = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, need, h->bt_cnt, h->bt_off, (int)n_ids + 1, h->stream);
+        if (need > h->bt_scan_bytes) {
+            cudaFree(h->bt_scan_tmp);
+            h->bt_scan_tmp = nullptr;
+            h->bt_scan_bytes = 0;
+            if (cudaMalloc(&h->bt_scan_tmp, need + 256) != cudaSuccess)
+                rc = fail(HPF_ENOMEM, "scan scratch allocation failed");
+            else
+                h->bt_scan_bytes = need + 256;
+        }
+        if (rc == HPF_OK) {
+            size_t bytes = h->bt_scan_bytes;
+            cub::DeviceScan::ExclusiveSum(h->bt_scan_tmp, bytes, h->bt_cnt, h->bt_off, (int)n_ids + 1, h->stream);
+            h->launches++;
+            cudaMemcpyAsync(&total, h->bt_off + n_ids, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+            cudaError_t e = cudaStreamSynchronize(h->stream);
+            if (e != cudaSuccess) rc = fail(HPF_ECUDA, "batch scan failed: %s", cudaGetErrorString(e));
+        }
+    }
+    cudaFree(d_bad);
+    if (rc != HPF_OK) return rc;
+
+    // compact triples of the batch (row after row, like get_i_batch_pass2) + stamps of the minor ids
+    if (total > h->bt_cap_nnz || !h->bt_major) {
+        int64_t c1 = 0, c2 = 0, c3 = 0;
+        TRY(grow_bytes((void**)&h->bt_major, &c1, total, sizeof(int)));
+        TRY(grow_bytes((void**)&h->bt_minor, &c2, total, sizeof(int)));
+        TRY(grow_bytes(&h->bt_val, &c3, total, (size_t)h->rb));
+        h->bt_cap_nnz = c1;
+    }
+    if (total > 0) {
+        long long want = ((long long)n_ids * 32 + 255) / 256;
+        if (want > 148 * 16) want = 148 * 16;
+        if (h->rb == 4)
+            hpf::batch_expand_kernel<float><<<(unsigned)want, 256, 0, h->stream>>>(
+                (int)n_ids, h->bt_ids, ptr, h->bt_off, src_minor, (const float*)src_val, h->bt_major, h->bt_minor,
+                (float*)h->bt_val, stamp_minor, step);
+        else
+            hpf::batch_expand_kernel<double><<<(unsigned)want, 256, 0, h->stream>>>(
+                (int)n_ids, h->bt_ids, ptr, h->bt_off, src_minor, (const double*)src_val, h->bt_major, h->bt_minor,
+                (double*)h->bt_val, stamp_minor, step);
+        h->launches++;
+        CKK();
+    }
+    const int* iu = ub ? h->bt_major : h->bt_minor;
+    const int* ii = ub ? h->bt_minor : h->bt_major;
+    return batch_core(h, iu, ii, h->bt_val, total, h->bt_ids, n_ids, nullptr, 0, ub, rho, mult, blend_all_rates != 0, step);
 }

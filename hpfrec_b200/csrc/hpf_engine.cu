@@ -7,6 +7,7 @@
 #include "hpf_sweep_tma.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <cstdarg>
 #include <cstdio>
@@ -106,6 +107,14 @@ struct hpf_engine {
     int *B_row = nullptr, *B_col = nullptr;  // item-major: row = item, col = user
     void* B_val = nullptr;
     bool data_loaded = false;
+    int last_panels = 1, panelsA = 1, panelsB = 1;
+    int *A_ptr = nullptr, *B_ptr = nullptr;  // CSR / CSC row pointers (only when both orderings are single-panel)
+    // grow-only scratch of the device-assembled minibatch (hpf_step_batch_ids)
+    int *bt_major = nullptr, *bt_minor = nullptr, *bt_cnt = nullptr, *bt_off = nullptr, *bt_ids = nullptr;
+    void* bt_val = nullptr;
+    void* bt_scan_tmp = nullptr;
+    size_t bt_scan_bytes = 0;
+    int64_t bt_cap_nnz = 0, bt_cap_ids = 0;
     // options
     double panel_mb = 48.0;
     int chunk = 64;
@@ -152,6 +161,9 @@ int free_data(hpf_engine* h) {
     cudaFree(h->B_row);
     cudaFree(h->B_col);
     cudaFree(h->B_val);
+    cudaFree(h->A_ptr);
+    cudaFree(h->B_ptr);
+    h->A_ptr = h->B_ptr = nullptr;
     h->A_row = h->A_col = h->B_row = h->B_col = nullptr;
     h->A_val = h->B_val = nullptr;
     h->data_loaded = false;
@@ -260,6 +272,7 @@ int build_order(hpf_engine* h, const int* major, const int* minor, const real* v
     const double minor_bytes = (double)n_minor * h->ld * h->rb;
     int panels = (int)((minor_bytes + h->panel_mb * 1048576.0 - 1.0) / (h->panel_mb * 1048576.0));
     if (panels < 1) panels = 1;
+    h->last_panels = panels;
     const int per_panel = (int)((n_minor + panels - 1) / panels);
     const unsigned long long span = (unsigned long long)(n_major > 0 ? n_major : 1);
     int end_bit = 1;
@@ -665,7 +678,8 @@ int hpf_destroy(hpf_engine* h) {
         if (e) cudaEventDestroy(e);
     for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
     h->ipc_opened.clear();
-    void* ptrs[] = {h->Gshp, h->Grte, h->Lshp, h->Lrte, h->krte, h->trte, h->xu, h->xi, h->accU, h->accI, h->Tsum, h->Bsum, h->stamp_u, h->stamp_i};
+    void* ptrs[] = {h->Gshp, h->Grte, h->Lshp, h->Lrte, h->krte, h->trte, h->xu, h->xi, h->accU, h->accI, h->Tsum, h->Bsum, h->stamp_u, h->stamp_i,
+                    h->bt_major, h->bt_minor, h->bt_cnt, h->bt_off, h->bt_ids, h->bt_val, h->bt_scan_tmp};
     for (void* p : ptrs) cudaFree(p);
     delete h;
     return HPF_OK;
@@ -837,10 +851,27 @@ int hpf_load_coo(hpf_engine* h, const void* ix_u, const void* ix_i, const void* 
     if (rc == HPF_OK) {
         if (h->rb == 4) {
             rc = build_order<float>(h, u32, i32, (const float*)yv, nnz, h->nU, h->nI, &h->A_row, &h->A_col, &h->A_val);
+            h->panelsA = h->last_panels;
             if (rc == HPF_OK) rc = build_order<float>(h, i32, u32, (const float*)yv, nnz, h->nI, h->nU, &h->B_row, &h->B_col, &h->B_val);
+            h->panelsB = h->last_panels;
         } else {
             rc = build_order<double>(h, u32, i32, (const double*)yv, nnz, h->nU, h->nI, &h->A_row, &h->A_col, &h->A_val);
+            h->panelsA = h->last_panels;
             if (rc == HPF_OK) rc = build_order<double>(h, i32, u32, (const double*)yv, nnz, h->nI, h->nU, &h->B_row, &h->B_col, &h->B_val);
+            h->panelsB = h->last_panels;
+        }
+    }
+    // single-panel orderings are plain CSR / CSC: keep their row pointers for device-side minibatch
+    // assembly (hpf_step_batch_ids)
+    if (rc == HPF_OK && h->panelsA == 1 && h->panelsB == 1) {
+        if (cudaMalloc(&h->A_ptr, sizeof(int) * (size_t)(h->nU + 1)) != cudaSuccess ||
+            cudaMalloc(&h->B_ptr, sizeof(int) * (size_t)(h->nI + 1)) != cudaSuccess) {
+            rc = fail(HPF_ENOMEM, "device allocation of row pointers failed");
+        } else {
+            hpf::row_ptr_kernel<<<nblk(nnz + 1), 256, 0, h->stream>>>(h->A_row, nnz, (int)h->nU, h->A_ptr);
+            hpf::row_ptr_kernel<<<nblk(nnz + 1), 256, 0, h->stream>>>(h->B_row, nnz, (int)h->nI, h->B_ptr);
+            h->launches += 2;
+            if (cudaGetLastError() != cudaSuccess) rc = fail(HPF_ECUDA, "row_ptr_kernel failed");
         }
     }
     cudaStreamSynchronize(h->stream);

@@ -209,6 +209,12 @@ class Engine:
             _ptr(users, name="users"), int(users.shape[0]), _ptr(items, name="items"), int(items.shape[0]),
             ib, int(bool(user_batch)), float(rho), float(mult), int(bool(blend_all_rates))))
 
+    def step_batch_ids(self, ids, user_batch, rho, mult, blend_all_rates=False):
+        """Minibatch update for the rows `ids` using the triples resident on the device."""
+        _lib.check(self._lib.hpf_step_batch_ids(self._h, _ptr(ids, name="ids"), int(ids.shape[0]), _index_bytes(ids),
+                                                int(bool(user_batch)), float(rho), float(mult),
+                                                int(bool(blend_all_rates))))
+
     # -- metrics / scoring --------------------------------------------------------------------------
     def llk(self, ix_u, ix_i, Y, full_llk=False):
         out = (ctypes.c_double * 4)()

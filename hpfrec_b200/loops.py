@@ -131,9 +131,11 @@ class CudaLoops:
             del state
             full_updates = (users_per_batch == 0) and (items_per_batch == 0)
             t_ingest = time.time()
-            if full_updates or (stop_crit in ("train-llk",)) or (verbose and not has_valset):
-                # the resident triples feed the sweep (full batch) and the training-llk checks
-                eng.load_coo(ix_u, ix_i, Y)
+            if not full_updates:
+                # minibatches are assembled on the device from plain CSR / CSC orderings (one panel)
+                eng.set_option("panel_mb", 1e9)
+            # the resident triples feed the sweep, the minibatch assembly and the training-llk checks
+            eng.load_coo(ix_u, ix_i, Y)
             t_ingest = time.time() - t_ingest
 
             if items_per_batch > 0:
@@ -141,13 +143,9 @@ class CudaLoops:
                     print("Creating item indices for stochastic optimization...")
                 items_numeration = np.arange(nI, dtype=np.int64)
                 nbatches_i = int(np.ceil(float(nI) / float(items_per_batch)))
-                st_ix_i, csc_u, csc_y = self.get_csc_data(ix_u, ix_i, Y, nU, nI)
             if users_per_batch != 0:
                 users_numeration = np.arange(nU, dtype=np.int64)
                 nbatches_u = int(np.ceil(float(nU) / float(users_per_batch)))
-                st_ix_u = np.asarray(st_ix_u).astype(np.int64)
-                ix_i64 = ix_i.astype(np.int64, copy=False)
-                ix_u64 = ix_u.astype(np.int64, copy=False)
 
             rng = np.random.default_rng(seed=random_seed if random_seed > 0 else None)   # pxi:207
             errs = [0.0, 0.0]
@@ -190,19 +188,13 @@ class CudaLoops:
                         for bt in range(nbatches_u):
                             users = users_numeration[bt * users_per_batch: min(nU, (bt + 1) * users_per_batch)]
                             mult = float(nU) / float(users.shape[0])                     # pxi:282
-                            pos, cnt = _rows_in_order(st_ix_u, users)
-                            ib = ix_i64[pos]
-                            eng.step_batch(ix_u64[pos], ib, Y[pos], np.ascontiguousarray(users),
-                                           np.unique(ib), True, rho, mult, False)
+                            eng.step_batch_ids(np.ascontiguousarray(users), True, rho, mult, False)
                     else:
                         rng.shuffle(items_numeration)                                    # pxi:329
                         for bt in range(nbatches_i):
                             items = items_numeration[bt * items_per_batch: min(nI, (bt + 1) * items_per_batch)]
                             mult = float(nI) / float(items.shape[0])                     # pxi:334
-                            pos, cnt = _rows_in_order(st_ix_i, items)
-                            ub = csc_u[pos]
-                            eng.step_batch(ub, np.repeat(items, cnt), csc_y[pos], np.unique(ub),
-                                           np.ascontiguousarray(items), False, rho, mult, False)
+                            eng.step_batch_ids(np.ascontiguousarray(items), False, rho, mult, False)
                     it_done += 1
                 i = it_done - 1
 

@@ -133,6 +133,14 @@ int hpf_step_batch(hpf_engine* h, const void* ix_u, const void* ix_i, const void
                    int32_t index_bytes, int32_t user_batch, double rho, double mult,
                    int32_t blend_all_rates);
 
+/* Same update for a batch given ONLY by its row ids (users if user_batch != 0, else items): the
+ * engine gathers the rows' triples from its resident orderings on the device and finds the unique
+ * opposite-side ids itself (replaces get_unique_items_batch / get_i_batch_pass1/2, pxi:27-42,
+ * 774-797, and the per-batch host -> device copy).  Requires hpf_load_coo to have run with a single
+ * L2 panel per side (option "panel_mb" >= size of the larger factor matrix).  ids: [h|d]. */
+int hpf_step_batch_ids(hpf_engine* h, const void* ids, int64_t n_ids, int32_t index_bytes,
+                       int32_t user_batch, double rho, double mult, int32_t blend_all_rates);
+
 /* ---- convergence metrics and scoring --------------------------- */
 
 /* llk_plus_rmse (pxi:627) over the given triples using the engine's current Theta/Beta:

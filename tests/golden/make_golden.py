@@ -126,5 +126,94 @@ def main():
     print("golden files written to", OUT, "|", ver)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--api" not in sys.argv:
     main()
+
+
+def load_reference_class():
+    """The reference's own `HPF` class (hpfrec/__init__.py) imported from /root/reference, with its
+    compiled submodules resolved from oracle/_ref (build container only)."""
+    import importlib.util
+    import types
+    ref_pkg = "/root/reference/hpfrec"
+    so_dir = os.path.join(ROOT, "oracle", "_ref", "hpfrec")
+    R.load(False)  # puts oracle/_ref on sys.path and imports hpfrec.cython_loops_double as a namespace pkg
+    for name in list(sys.modules):
+        if name == "hpfrec" or name.startswith("hpfrec."):
+            del sys.modules[name]
+    chk = types.ModuleType("hpfrec._check_openmp")
+    chk.get = lambda: 1
+    spec = importlib.util.spec_from_file_location("hpfrec", os.path.join(ref_pkg, "__init__.py"),
+                                                  submodule_search_locations=[ref_pkg, so_dir])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["hpfrec"] = mod
+    sys.modules["hpfrec._check_openmp"] = chk
+    spec.loader.exec_module(mod)
+    return mod.HPF
+
+
+def api_golden():
+    """README flow through the reference's Python class (fp64, fixed seeds): fit with reindexing,
+    predict / topN / eval_llk, train-llk stopping, partial_fit sequence, predict_factors."""
+    import warnings
+    import pandas as pd
+    HPF = load_reference_class()
+    df = O.readme_toy()
+    out = {"versions": versions()}
+    warnings.simplefilter("ignore")
+    # string ids so that reindexing really happens
+    dfs = df.copy()
+    dfs["UserId"] = "u" + dfs["UserId"].astype(str)
+    dfs["ItemId"] = "i" + dfs["ItemId"].astype(str)
+    m = HPF(k=8, use_float=False, random_seed=7, maxiter=30, verbose=False, ncores=1, check_every=None)
+    m.fit(dfs.copy())
+    out["fit_Theta"], out["fit_Beta"] = m.Theta, m.Beta
+    out["fit_user_mapping"] = np.array(m.user_mapping_, dtype="U8")
+    out["fit_item_mapping"] = np.array(m.item_mapping_, dtype="U8")
+    out["fit_niter"] = m.niter
+    out["pred_single"] = m.predict(user="u10", item="i11")
+    out["pred_many"] = m.predict(user=["u10", "u11", "u12", "zz"], item=["i4", "i5", "i6", "i1"])
+    out["topn_seen"] = np.array(m.topN(user="u10", n=10, exclude_seen=True), dtype="U8")
+    out["topn_all"] = np.array(m.topN(user="u10", n=10, exclude_seen=False), dtype="U8")
+    out["topn_pool"] = np.array(m.topN(user="u10", n=3, exclude_seen=False,
+                                       items_pool=np.array(["i1", "i2", "i3", "i4", "i50"])), dtype="U8")
+    llk = m.eval_llk(dfs.copy(), full_llk=True)
+    out["eval_llk"], out["eval_nobs"] = np.float64(llk["llk"]), llk["nobs"]
+    # train-llk stopping criterion (niter tells where it stopped)
+    m2 = HPF(k=8, use_float=False, random_seed=7, maxiter=100, verbose=False, ncores=1, stop_crit="train-llk",
+             check_every=5, stop_thr=1e-3, reindex=False)
+    m2.fit(df.copy())
+    out["llkstop_niter"], out["llkstop_Theta"] = m2.niter, m2.Theta
+    # diff-norm criterion
+    m3 = HPF(k=8, use_float=False, random_seed=7, maxiter=100, verbose=False, ncores=1, stop_crit="diff-norm",
+             check_every=5, stop_thr=0.5, reindex=False)
+    m3.fit(df.copy())
+    out["normstop_niter"], out["normstop_Theta"] = m3.niter, m3.Theta
+    # public partial_fit sequence on a fresh object (README.md:116-123)
+    np.random.seed(3)
+    m4 = HPF(k=8, use_float=False, random_seed=7, reindex=False, keep_data=False, verbose=False, ncores=1)
+    batches = [np.unique(np.random.randint(100, size=20)) for _ in range(3)]
+    m4.partial_fit(df.loc[df.UserId.isin(batches[0])].copy(), nusers=100, nitems=100)
+    m4.partial_fit(df.loc[df.UserId.isin(batches[1])].copy())
+    m4.partial_fit(df.loc[df.ItemId.isin(batches[2])].copy(), batch_type="items")
+    for j, b in enumerate(batches):
+        out["pf_batch%d" % j] = b
+    out["pf_Theta"], out["pf_Beta"], out["pf_k_rte"], out["pf_niter"] = m4.Theta, m4.Beta, m4.k_rte, m4.niter
+    # predict_factors for a new user (README.md:135-143), on the fitted reindex=False model m2
+    np.random.seed(2)
+    new = pd.DataFrame({"ItemId": np.random.choice(np.arange(100), size=20, replace=False),
+                        "Count": np.random.gamma(1, 1, size=20).astype("int32")})
+    new = new.loc[new.Count > 0].reset_index(drop=True)
+    out["new_items"], out["new_counts"] = new.ItemId.to_numpy(), new.Count.to_numpy()
+    out["new_factors"] = m2.predict_factors(new.copy(), maxiter=10, random_seed=1)
+    # SVI through the class (ncores=1 for determinism)
+    m5 = HPF(k=8, use_float=False, random_seed=7, maxiter=6, verbose=False, ncores=1, users_per_batch=20,
+             items_per_batch=30, reindex=False, check_every=None)
+    m5.fit(df.copy())
+    out["svi_Theta"], out["svi_Beta"] = m5.Theta, m5.Beta
+    np.savez_compressed(os.path.join(OUT, "toy_api.npz"), **out)
+    print("toy_api.npz written")
+
+
+if __name__ == "__main__" and "--api" in sys.argv:
+    api_golden()
