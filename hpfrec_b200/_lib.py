@@ -46,6 +46,7 @@ SIGNATURES = {
     "hpf_update_shapes": ([_I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I32, _D, _D],
                           _c.c_int),
     "hpf_digamma": ([_I32, _I32, _P, _P, _I64], _c.c_int),
+    "hpf_trim_cache": ([], _c.c_int),
     "hpf_launch_count": ([_P, _c.POINTER(_I64)], _c.c_int),
     "hpf_phase_ms": ([_P, _c.POINTER(_D), _c.POINTER(_I64)], _c.c_int),
     "hpf_ld": ([_P, _c.POINTER(_I32)], _c.c_int),

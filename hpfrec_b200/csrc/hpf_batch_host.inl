@@ -9,8 +9,8 @@ namespace {
 
 int ensure_stamps(hpf_engine* h) {
     if (h->stamp_u) return HPF_OK;
-    CK(cudaMalloc(&h->stamp_u, sizeof(int) * (size_t)(h->nU > 0 ? h->nU : 1)));
-    CK(cudaMalloc(&h->stamp_i, sizeof(int) * (size_t)(h->nI > 0 ? h->nI : 1)));
+    CK(hpf_malloc(&h->stamp_u, sizeof(int) * (size_t)(h->nU > 0 ? h->nU : 1)));
+    CK(hpf_malloc(&h->stamp_i, sizeof(int) * (size_t)(h->nI > 0 ? h->nI : 1)));
     CK(cudaMemsetAsync(h->stamp_u, 0, sizeof(int) * (size_t)(h->nU > 0 ? h->nU : 1), h->stream));
     CK(cudaMemsetAsync(h->stamp_i, 0, sizeof(int) * (size_t)(h->nI > 0 ? h->nI : 1), h->stream));
     h->batch_step = 0;
@@ -96,10 +96,10 @@ int batch_core(hpf_engine* h, const int* iu, const int* ii, const void* yv, int6
 // grow-only device scratch
 int grow_bytes(void** p, int64_t* cap_elems, int64_t need_elems, size_t elem) {
     if (*p != nullptr && need_elems <= *cap_elems) return HPF_OK;
-    cudaFree(*p);
+    hpf_free(*p);
     *p = nullptr;
     const int64_t n = need_elems + need_elems / 4 + 16;
-    CK(cudaMalloc(p, (size_t)n * elem));
+    CK(hpf_malloc(p, (size_t)n * elem));
     *cap_elems = n;
     return HPF_OK;
 }
@@ -127,7 +127,7 @@ extern "C" int hpf_step_batch(hpf_engine* h, const void* ix_u, const void* ix_i,
     const void* yv = nullptr;
     int rc = HPF_OK;
     auto alloc_i = [&](int** p, int64_t n) {
-        if (rc == HPF_OK && cudaMalloc(p, sizeof(int) * (size_t)(n > 0 ? n : 1)) != cudaSuccess)
+        if (rc == HPF_OK && hpf_malloc(p, sizeof(int) * (size_t)(n > 0 ? n : 1)) != cudaSuccess)
             rc = fail(HPF_ENOMEM, "device allocation failed in hpf_step_batch");
     };
     alloc_i(&u32, nnz);
@@ -154,12 +154,12 @@ extern "C" int hpf_step_batch(hpf_engine* h, const void* ix_u, const void* ix_i,
     }
     cudaError_t e = cudaStreamSynchronize(h->stream);
     if (rc == HPF_OK && e != cudaSuccess) rc = fail(HPF_ECUDA, "minibatch kernels failed: %s", cudaGetErrorString(e));
-    cudaFree(u32);
-    cudaFree(i32);
-    cudaFree(ulist);
-    cudaFree(ilist);
-    cudaFree(d_bad);
-    cudaFree(yfree);
+    hpf_free(u32);
+    hpf_free(i32);
+    hpf_free(ulist);
+    hpf_free(ilist);
+    hpf_free(d_bad);
+    hpf_free(yfree);
     return rc;
 }
 
@@ -194,7 +194,7 @@ extern "C" int hpf_step_batch_ids(hpf_engine* h, const void* ids, int64_t n_ids,
         h->bt_cap_ids = c1;
     }
     int* d_bad = nullptr;
-    CK(cudaMalloc(&d_bad, 4));
+    CK(hpf_malloc(&d_bad, 4));
     cudaMemsetAsync(d_bad, 0, 4, h->stream);
     int rc = stage_index(h, ids, n_ids, index_bytes, n_major, h->bt_ids, d_bad);
     int total = 0;
@@ -211,10 +211,10 @@ extern "C" int hpf_step_batch_ids(hpf_engine* h, const void* ids, int64_t n_ids,
         size_t need = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, need, h->bt_cnt, h->bt_off, (int)n_ids + 1, h->stream);
         if (need > h->bt_scan_bytes) {
-            cudaFree(h->bt_scan_tmp);
+            hpf_free(h->bt_scan_tmp);
             h->bt_scan_tmp = nullptr;
             h->bt_scan_bytes = 0;
-            if (cudaMalloc(&h->bt_scan_tmp, need + 256) != cudaSuccess)
+            if (hpf_malloc(&h->bt_scan_tmp, need + 256) != cudaSuccess)
                 rc = fail(HPF_ENOMEM, "scan scratch allocation failed");
             else
                 h->bt_scan_bytes = need + 256;
@@ -228,7 +228,7 @@ extern "C" int hpf_step_batch_ids(hpf_engine* h, const void* ids, int64_t n_ids,
             if (e != cudaSuccess) rc = fail(HPF_ECUDA, "batch scan failed: %s", cudaGetErrorString(e));
         }
     }
-    cudaFree(d_bad);
+    hpf_free(d_bad);
     if (rc != HPF_OK) return rc;
 
     // compact triples of the batch (row after row, like get_i_batch_pass2) + stamps of the minor ids

@@ -11,8 +11,12 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 namespace {
@@ -80,6 +84,91 @@ bool is_device_ptr(const void* p) {
 }
 
 inline unsigned nblk(long long n, int t = 256) { return (unsigned)((n + t - 1) / t); }
+
+// -------------------------------------------------------------------------------------------------
+// Caching device allocator.  cudaMalloc / cudaFree of the engine's multi-hundred-MB buffers cost tens
+// of milliseconds per fit (cudaFree also synchronises the device); repeated fits in one process
+// (hyper-parameter sweeps, partial_fit loops, the bench's end-to-end call) reuse blocks instead.
+// Blocks are matched by exact (device, rounded size); the cache is capped (HPF_CACHE_MB, default
+// 32768) and can be released with hpf_trim_cache().  All frees in this file happen after the stream
+// that used the block has been synchronised, so immediate reuse is safe.
+// -------------------------------------------------------------------------------------------------
+struct DevCache {
+    std::mutex mu;
+    std::multimap<std::pair<int, size_t>, void*> free_blocks;
+    std::unordered_map<void*, std::pair<int, size_t>> live;
+    size_t cached_bytes = 0;
+    size_t cap_bytes = 0;
+    bool cap_init = false;
+};
+DevCache g_cache;
+
+inline size_t round_block(size_t bytes) { return (bytes + 511) & ~(size_t)511; }
+
+cudaError_t hpf_malloc_impl(void** p, size_t bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const size_t rb = round_block(bytes > 0 ? bytes : 1);
+    {
+        std::lock_guard<std::mutex> lk(g_cache.mu);
+        auto it = g_cache.free_blocks.find({dev, rb});
+        if (it != g_cache.free_blocks.end()) {
+            *p = it->second;
+            g_cache.free_blocks.erase(it);
+            g_cache.cached_bytes -= rb;
+            g_cache.live[*p] = {dev, rb};
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(p, rb);
+    if (e == cudaErrorMemoryAllocation) {  // give cached blocks back to the driver and retry once
+        cudaGetLastError();
+        std::vector<void*> drop;
+        {
+            std::lock_guard<std::mutex> lk(g_cache.mu);
+            for (auto& kv : g_cache.free_blocks) drop.push_back(kv.second);
+            g_cache.free_blocks.clear();
+            g_cache.cached_bytes = 0;
+        }
+        for (void* q : drop) cudaFree(q);
+        e = cudaMalloc(p, rb);
+    }
+    if (e == cudaSuccess) {
+        std::lock_guard<std::mutex> lk(g_cache.mu);
+        g_cache.live[*p] = {dev, rb};
+    }
+    return e;
+}
+template <typename T>
+cudaError_t hpf_malloc(T** p, size_t bytes) {
+    return hpf_malloc_impl((void**)p, bytes);
+}
+
+void hpf_free(void* p) {
+    if (!p) return;
+    std::pair<int, size_t> info;
+    {
+        std::lock_guard<std::mutex> lk(g_cache.mu);
+        if (!g_cache.cap_init) {
+            const char* env = getenv("HPF_CACHE_MB");
+            g_cache.cap_bytes = (size_t)(env ? atof(env) : 32768.0) * 1048576ull;
+            g_cache.cap_init = true;
+        }
+        auto it = g_cache.live.find(p);
+        if (it == g_cache.live.end()) {  // not ours (should not happen)
+            cudaFree(p);
+            return;
+        }
+        info = it->second;
+        g_cache.live.erase(it);
+        if (g_cache.cached_bytes + info.second <= g_cache.cap_bytes) {
+            g_cache.free_blocks.insert({info, p});
+            g_cache.cached_bytes += info.second;
+            return;
+        }
+    }
+    cudaFree(p);
+}
 
 }  // namespace
 
@@ -155,14 +244,14 @@ struct DeviceGuard {
 };
 
 int free_data(hpf_engine* h) {
-    cudaFree(h->A_row);
-    cudaFree(h->A_col);
-    cudaFree(h->A_val);
-    cudaFree(h->B_row);
-    cudaFree(h->B_col);
-    cudaFree(h->B_val);
-    cudaFree(h->A_ptr);
-    cudaFree(h->B_ptr);
+    hpf_free(h->A_row);
+    hpf_free(h->A_col);
+    hpf_free(h->A_val);
+    hpf_free(h->B_row);
+    hpf_free(h->B_col);
+    hpf_free(h->B_val);
+    hpf_free(h->A_ptr);
+    hpf_free(h->B_ptr);
     h->A_ptr = h->B_ptr = nullptr;
     h->A_row = h->A_col = h->B_row = h->B_col = nullptr;
     h->A_val = h->B_val = nullptr;
@@ -186,10 +275,10 @@ int stage_in(hpf_engine* h, const void* src, size_t bytes, const void** dev, voi
         return HPF_OK;
     }
     void* tmp = nullptr;
-    CK(cudaMalloc(&tmp, bytes));
+    CK(hpf_malloc(&tmp, bytes));
     cudaError_t e = cudaMemcpyAsync(tmp, src, bytes, cudaMemcpyHostToDevice, h->stream);
     if (e != cudaSuccess) {
-        cudaFree(tmp);
+        hpf_free(tmp);
         return fail(HPF_ECUDA, "H2D copy failed: %s", cudaGetErrorString(e));
     }
     *dev = tmp;
@@ -213,7 +302,7 @@ int stage_index(hpf_engine* h, const void* src, int64_t n, int index_bytes, int6
     cudaError_t e = cudaGetLastError();
     if (tmp) {
         cudaStreamSynchronize(h->stream);
-        cudaFree(tmp);
+        hpf_free(tmp);
     }
     if (e != cudaSuccess) return fail(HPF_ECUDA, "index conversion failed: %s", cudaGetErrorString(e));
     return HPF_OK;
@@ -231,7 +320,7 @@ int upload_matrix(hpf_engine* h, const void* src, void* dst, int64_t nrows, int 
     cudaError_t e = cudaGetLastError();
     if (tmp) {
         cudaStreamSynchronize(h->stream);
-        cudaFree(tmp);
+        hpf_free(tmp);
     }
     if (e != cudaSuccess) return fail(HPF_ECUDA, "pad_rows failed: %s", cudaGetErrorString(e));
     return HPF_OK;
@@ -247,7 +336,7 @@ int download_matrix(hpf_engine* h, const void* src, const void* denom, void* dst
     void* tmp = nullptr;
     real* out = (real*)dst;
     if (!dev_dst) {
-        CK(cudaMalloc(&tmp, bytes));
+        CK(hpf_malloc(&tmp, bytes));
         out = (real*)tmp;
     }
     hpf::unpad_rows_kernel<real><<<nblk(nrows * k), 256, 0, h->stream>>>((const real*)src, (const real*)denom, out, nrows, k, ld);
@@ -255,7 +344,7 @@ int download_matrix(hpf_engine* h, const void* src, const void* denom, void* dst
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && !dev_dst) e = cudaMemcpyAsync(dst, tmp, bytes, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    if (tmp) cudaFree(tmp);
+    if (tmp) hpf_free(tmp);
     if (e != cudaSuccess) return fail(HPF_ECUDA, "export failed: %s", cudaGetErrorString(e));
     return HPF_OK;
 }
@@ -264,9 +353,9 @@ int download_matrix(hpf_engine* h, const void* src, const void* denom, void* dst
 template <typename real>
 int build_order(hpf_engine* h, const int* major, const int* minor, const real* val, int64_t n,
                 int64_t n_major, int64_t n_minor, int** o_row, int** o_col, void** o_val) {
-    CK(cudaMalloc(o_row, sizeof(int) * (size_t)(n > 0 ? n : 1)));
-    CK(cudaMalloc(o_col, sizeof(int) * (size_t)(n > 0 ? n : 1)));
-    CK(cudaMalloc(o_val, sizeof(real) * (size_t)(n > 0 ? n : 1)));
+    CK(hpf_malloc(o_row, sizeof(int) * (size_t)(n > 0 ? n : 1)));
+    CK(hpf_malloc(o_col, sizeof(int) * (size_t)(n > 0 ? n : 1)));
+    CK(hpf_malloc(o_val, sizeof(real) * (size_t)(n > 0 ? n : 1)));
     if (n == 0) return HPF_OK;
     // panels: the gathered (minor) factor matrix is cut so one panel stays L2-resident
     const double minor_bytes = (double)n_minor * h->ld * h->rb;
@@ -287,17 +376,17 @@ int build_order(hpf_engine* h, const int* major, const int* minor, const real* v
 #define OCK(call)                                                                        \
     if (rc == HPF_OK && (e = (call)) != cudaSuccess)                                     \
     rc = fail(e == cudaErrorMemoryAllocation ? HPF_ENOMEM : HPF_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e))
-    OCK(cudaMalloc(&k_in, 8 * (size_t)n));
-    OCK(cudaMalloc(&k_out, 8 * (size_t)n));
-    OCK(cudaMalloc(&p_in, 4 * (size_t)n));
-    OCK(cudaMalloc(&p_out, 4 * (size_t)n));
+    OCK(hpf_malloc(&k_in, 8 * (size_t)n));
+    OCK(hpf_malloc(&k_out, 8 * (size_t)n));
+    OCK(hpf_malloc(&p_in, 4 * (size_t)n));
+    OCK(hpf_malloc(&p_out, 4 * (size_t)n));
     if (rc == HPF_OK) {
         hpf::make_keys_kernel<<<nblk(n), 256, 0, h->stream>>>(major, minor, n, per_panel, span, k_in, p_in);
         h->launches++;
     }
     OCK(cudaGetLastError());
     OCK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, p_in, p_out, (int)n, 0, end_bit, h->stream));
-    OCK(cudaMalloc(&tmp, tmp_bytes > 0 ? tmp_bytes : 16));
+    OCK(hpf_malloc(&tmp, tmp_bytes > 0 ? tmp_bytes : 16));
     OCK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, p_in, p_out, (int)n, 0, end_bit, h->stream));
     if (rc == HPF_OK) {
         hpf::apply_order_kernel<real><<<nblk(n), 256, 0, h->stream>>>(k_out, p_out, n, span, minor, val, *o_row, *o_col, (real*)*o_val);
@@ -306,11 +395,11 @@ int build_order(hpf_engine* h, const int* major, const int* minor, const real* v
     OCK(cudaGetLastError());
     OCK(cudaStreamSynchronize(h->stream));
 #undef OCK
-    cudaFree(k_in);
-    cudaFree(k_out);
-    cudaFree(p_in);
-    cudaFree(p_out);
-    cudaFree(tmp);
+    hpf_free(k_in);
+    hpf_free(k_out);
+    hpf_free(p_in);
+    hpf_free(p_out);
+    hpf_free(tmp);
     return rc;
 }
 
@@ -650,13 +739,13 @@ int hpf_create(hpf_engine** out, int64_t nU, int64_t nI, int32_t k, int32_t real
     void** mats_u[] = {&h->Gshp, &h->Grte, &h->xu, &h->accU};
     void** mats_i[] = {&h->Lshp, &h->Lrte, &h->xi, &h->accI};
     for (auto p : mats_u)
-        if (e == cudaSuccess) e = cudaMalloc(p, mu);
+        if (e == cudaSuccess) e = hpf_malloc(p, mu);
     for (auto p : mats_i)
-        if (e == cudaSuccess) e = cudaMalloc(p, mi);
-    if (e == cudaSuccess) e = cudaMalloc(&h->krte, (size_t)(nU > 0 ? nU : 1) * real_bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&h->trte, (size_t)(nI > 0 ? nI : 1) * real_bytes);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&h->Tsum, sizeof(double) * ld);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&h->Bsum, sizeof(double) * ld);
+        if (e == cudaSuccess) e = hpf_malloc(p, mi);
+    if (e == cudaSuccess) e = hpf_malloc(&h->krte, (size_t)(nU > 0 ? nU : 1) * real_bytes);
+    if (e == cudaSuccess) e = hpf_malloc(&h->trte, (size_t)(nI > 0 ? nI : 1) * real_bytes);
+    if (e == cudaSuccess) e = hpf_malloc((void**)&h->Tsum, sizeof(double) * ld);
+    if (e == cudaSuccess) e = hpf_malloc((void**)&h->Bsum, sizeof(double) * ld);
     if (e == cudaSuccess) e = cudaMemset(h->Tsum, 0, sizeof(double) * ld);
     if (e == cudaSuccess) e = cudaMemset(h->Bsum, 0, sizeof(double) * ld);
     if (e != cudaSuccess) {
@@ -680,7 +769,7 @@ int hpf_destroy(hpf_engine* h) {
     h->ipc_opened.clear();
     void* ptrs[] = {h->Gshp, h->Grte, h->Lshp, h->Lrte, h->krte, h->trte, h->xu, h->xi, h->accU, h->accI, h->Tsum, h->Bsum, h->stamp_u, h->stamp_i,
                     h->bt_major, h->bt_minor, h->bt_cnt, h->bt_off, h->bt_ids, h->bt_val, h->bt_scan_tmp};
-    for (void* p : ptrs) cudaFree(p);
+    for (void* p : ptrs) hpf_free(p);
     delete h;
     return HPF_OK;
 }
@@ -828,14 +917,14 @@ int hpf_load_coo(hpf_engine* h, const void* ix_u, const void* ix_i, const void* 
     const void* yv = nullptr;
     int rc = HPF_OK;
     auto cleanup = [&]() {
-        cudaFree(u32);
-        cudaFree(i32);
-        cudaFree(d_bad);
-        if (to_free) cudaFree(to_free);
+        hpf_free(u32);
+        hpf_free(i32);
+        hpf_free(d_bad);
+        if (to_free) hpf_free(to_free);
     };
     const size_t n1 = (size_t)(nnz > 0 ? nnz : 1);
-    if (cudaMalloc(&u32, 4 * n1) != cudaSuccess || cudaMalloc(&i32, 4 * n1) != cudaSuccess ||
-        cudaMalloc(&d_bad, 4) != cudaSuccess) {
+    if (hpf_malloc(&u32, 4 * n1) != cudaSuccess || hpf_malloc(&i32, 4 * n1) != cudaSuccess ||
+        hpf_malloc(&d_bad, 4) != cudaSuccess) {
         cleanup();
         h->nnz = 0;
         return fail(HPF_ENOMEM, "device allocation failed in hpf_load_coo");
@@ -864,8 +953,8 @@ int hpf_load_coo(hpf_engine* h, const void* ix_u, const void* ix_i, const void* 
     // single-panel orderings are plain CSR / CSC: keep their row pointers for device-side minibatch
     // assembly (hpf_step_batch_ids)
     if (rc == HPF_OK && h->panelsA == 1 && h->panelsB == 1) {
-        if (cudaMalloc(&h->A_ptr, sizeof(int) * (size_t)(h->nU + 1)) != cudaSuccess ||
-            cudaMalloc(&h->B_ptr, sizeof(int) * (size_t)(h->nI + 1)) != cudaSuccess) {
+        if (hpf_malloc(&h->A_ptr, sizeof(int) * (size_t)(h->nU + 1)) != cudaSuccess ||
+            hpf_malloc(&h->B_ptr, sizeof(int) * (size_t)(h->nI + 1)) != cudaSuccess) {
             rc = fail(HPF_ENOMEM, "device allocation of row pointers failed");
         } else {
             hpf::row_ptr_kernel<<<nblk(nnz + 1), 256, 0, h->stream>>>(h->A_row, nnz, (int)h->nU, h->A_ptr);
@@ -1048,6 +1137,18 @@ int hpf_beta_colsum(hpf_engine* h, void** ptr, int64_t* count) {
     return HPF_OK;
 }
 
+int hpf_trim_cache(void) {
+    std::vector<void*> drop;
+    {
+        std::lock_guard<std::mutex> lk(g_cache.mu);
+        for (auto& kv : g_cache.free_blocks) drop.push_back(kv.second);
+        g_cache.free_blocks.clear();
+        g_cache.cached_bytes = 0;
+    }
+    for (void* q : drop) cudaFree(q);
+    return HPF_OK;
+}
+
 int hpf_launch_count(hpf_engine* h, int64_t* out) {
     if (!h || !out) return fail(HPF_EINVAL, "NULL argument");
     *out = h->launches;
@@ -1075,9 +1176,9 @@ static int score_common(hpf_engine* h, const int* iu, const int* ii, const void*
     void *theta = nullptr, *beta = nullptr;
     double* d_sums = nullptr;
     int rc = HPF_OK;
-    cudaError_t e = cudaMalloc(&theta, h->mat_bytes(h->nU > 0 ? h->nU : 1));
-    if (e == cudaSuccess) e = cudaMalloc(&beta, h->mat_bytes(h->nI > 0 ? h->nI : 1));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&d_sums, sizeof(double) * (4 + 2 * (size_t)h->ld));
+    cudaError_t e = hpf_malloc(&theta, h->mat_bytes(h->nU > 0 ? h->nU : 1));
+    if (e == cudaSuccess) e = hpf_malloc(&beta, h->mat_bytes(h->nI > 0 ? h->nI : 1));
+    if (e == cudaSuccess) e = hpf_malloc((void**)&d_sums, sizeof(double) * (4 + 2 * (size_t)h->ld));
     if (e == cudaSuccess) e = cudaMemsetAsync(d_sums, 0, sizeof(double) * (4 + 2 * (size_t)h->ld), h->stream);
     if (e != cudaSuccess) rc = fail(HPF_ENOMEM, "scratch allocation failed: %s", cudaGetErrorString(e));
     if (rc == HPF_OK) {
@@ -1115,9 +1216,9 @@ static int score_common(hpf_engine* h, const int* iu, const int* ii, const void*
     }
     e = cudaStreamSynchronize(h->stream);
     if (rc == HPF_OK && e != cudaSuccess) rc = fail(HPF_ECUDA, "score kernels failed: %s", cudaGetErrorString(e));
-    cudaFree(theta);
-    cudaFree(beta);
-    cudaFree(d_sums);
+    hpf_free(theta);
+    hpf_free(beta);
+    hpf_free(d_sums);
     return rc;
 }
 
@@ -1139,7 +1240,7 @@ static int score_external(hpf_engine* h, const void* ix_u, const void* ix_i, con
     const void* yv = nullptr;
     const size_t n1 = (size_t)(n > 0 ? n : 1);
     int rc = HPF_OK;
-    if (cudaMalloc(&u32, 4 * n1) != cudaSuccess || cudaMalloc(&i32, 4 * n1) != cudaSuccess || cudaMalloc(&d_bad, 4) != cudaSuccess)
+    if (hpf_malloc(&u32, 4 * n1) != cudaSuccess || hpf_malloc(&i32, 4 * n1) != cudaSuccess || hpf_malloc(&d_bad, 4) != cudaSuccess)
         rc = fail(HPF_ENOMEM, "device allocation failed");
     if (rc == HPF_OK) {
         cudaMemsetAsync(d_bad, 0, 4, h->stream);
@@ -1154,18 +1255,18 @@ static int score_external(hpf_engine* h, const void* ix_u, const void* ix_i, con
         if (bad) rc = fail(HPF_EINVAL, "index out of range");
     }
     const bool pred_is_dev = pred_out && is_device_ptr(pred_out);
-    if (rc == HPF_OK && pred_out && !pred_is_dev && cudaMalloc(&pred_dev, n1 * h->rb) != cudaSuccess)
+    if (rc == HPF_OK && pred_out && !pred_is_dev && hpf_malloc(&pred_dev, n1 * h->rb) != cudaSuccess)
         rc = fail(HPF_ENOMEM, "device allocation failed");
     if (rc == HPF_OK) rc = score_common(h, u32, i32, yv, n, full_llk, out4, pred_out ? (pred_is_dev ? pred_out : pred_dev) : nullptr);
     if (rc == HPF_OK && pred_dev && n > 0) {
         if (cudaMemcpy(pred_out, pred_dev, (size_t)n * h->rb, cudaMemcpyDeviceToHost) != cudaSuccess)
             rc = fail(HPF_ECUDA, "D2H of predictions failed");
     }
-    cudaFree(u32);
-    cudaFree(i32);
-    cudaFree(d_bad);
-    cudaFree(yfree);
-    cudaFree(pred_dev);
+    hpf_free(u32);
+    hpf_free(i32);
+    hpf_free(d_bad);
+    hpf_free(yfree);
+    hpf_free(pred_dev);
     return rc;
 }
 
@@ -1199,7 +1300,7 @@ int hpf_update_shapes(int32_t real_bytes, int32_t index_bytes, int32_t device, v
         std::vector<char> ones((size_t)(nU > nI ? nU : nI) * real_bytes + 8, 0);
         if ((rc = hpf_load_state(h, G_sh, G_rt, L_sh, L_rt, ones.data(), ones.data())) != HPF_OK) break;
         if ((rc = ensure_x(h)) != HPF_OK) break;
-        if (cudaMalloc(&u32, 4 * n1) != cudaSuccess || cudaMalloc(&i32, 4 * n1) != cudaSuccess || cudaMalloc(&d_bad, 4) != cudaSuccess) {
+        if (hpf_malloc(&u32, 4 * n1) != cudaSuccess || hpf_malloc(&i32, 4 * n1) != cudaSuccess || hpf_malloc(&d_bad, 4) != cudaSuccess) {
             rc = fail(HPF_ENOMEM, "device allocation failed");
             break;
         }
@@ -1214,7 +1315,7 @@ int hpf_update_shapes(int32_t real_bytes, int32_t index_bytes, int32_t device, v
             break;
         }
         const bool phi_dev_dst = phi && is_device_ptr(phi);
-        if (phi && !phi_dev_dst && cudaMalloc(&phi_dev, n1 * (size_t)k * real_bytes) != cudaSuccess) {
+        if (phi && !phi_dev_dst && hpf_malloc(&phi_dev, n1 * (size_t)k * real_bytes) != cudaSuccess) {
             rc = fail(HPF_ENOMEM, "device allocation of phi failed");
             break;
         }
@@ -1234,13 +1335,13 @@ int hpf_update_shapes(int32_t real_bytes, int32_t index_bytes, int32_t device, v
             rc = fail(HPF_ECUDA, "D2H of phi failed");
     } while (0);
     std::string keep = g_err;
-    cudaFree(kr);
-    cudaFree(tr);
-    cudaFree(phi_dev);
-    cudaFree(u32);
-    cudaFree(i32);
-    cudaFree(d_bad);
-    cudaFree(yfree);
+    hpf_free(kr);
+    hpf_free(tr);
+    hpf_free(phi_dev);
+    hpf_free(u32);
+    hpf_free(i32);
+    hpf_free(d_bad);
+    hpf_free(yfree);
     hpf_destroy(h);
     g_err = keep;
     return rc;
@@ -1259,7 +1360,7 @@ int hpf_digamma(int32_t real_bytes, int32_t device, const void* x, void* out, in
     void *dx = nullptr, *dout = nullptr;
     const size_t bytes = (size_t)n * real_bytes;
     int rc = HPF_OK;
-    if (cudaMalloc(&dx, bytes) != cudaSuccess || cudaMalloc(&dout, bytes) != cudaSuccess) rc = fail(HPF_ENOMEM, "device allocation failed");
+    if (hpf_malloc(&dx, bytes) != cudaSuccess || hpf_malloc(&dout, bytes) != cudaSuccess) rc = fail(HPF_ENOMEM, "device allocation failed");
     if (rc == HPF_OK && cudaMemcpy(dx, x, bytes, cudaMemcpyDefault) != cudaSuccess) rc = fail(HPF_ECUDA, "copy in failed");
     if (rc == HPF_OK) {
         if (real_bytes == 4)
@@ -1269,8 +1370,8 @@ int hpf_digamma(int32_t real_bytes, int32_t device, const void* x, void* out, in
         if (cudaGetLastError() != cudaSuccess || cudaMemcpy(out, dout, bytes, cudaMemcpyDefault) != cudaSuccess)
             rc = fail(HPF_ECUDA, "digamma kernel failed");
     }
-    cudaFree(dx);
-    cudaFree(dout);
+    hpf_free(dx);
+    hpf_free(dout);
     return rc;
 }
 

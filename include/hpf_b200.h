@@ -168,6 +168,9 @@ int hpf_update_shapes(int32_t real_bytes, int32_t index_bytes, int32_t device,
 /* Device digamma used by the engine, exposed for validation against scipy.special.psi. [h|d] */
 int hpf_digamma(int32_t real_bytes, int32_t device, const void* x, void* out, int64_t n);
 
+/* Releases the device blocks the library caches between engines (see the caching allocator in
+ * hpf_engine.cu; cap: environment variable HPF_CACHE_MB, default 32768). */
+int hpf_trim_cache(void);
 /* Counters for bench/telemetry: number of kernels this engine has launched so far. */
 int hpf_launch_count(hpf_engine* h, int64_t* out);
 /* With option "timing"=1: accumulated device milliseconds of the four kernels of a full-batch
