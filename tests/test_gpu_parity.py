@@ -306,3 +306,88 @@ def test_medium_size_vs_compiled_reference():
     out = _fit_gpu(y, u, i, nU, nI, k, 5, 123, panel_mb=1.0)
     for key in STATE_KEYS:
         assert relerr(out[key], r[key]) < 1e-9, key
+
+
+@pytest.mark.parametrize("k,dtype", [(200, np.float32), (400, np.float32), (200, np.float64)])
+def test_wide_rows_vs_oracle(k, dtype):
+    """Row lengths beyond 512 bytes (32-lane groups with 2 and 4 packs per lane)."""
+    nU, nI, nnz = 150, 90, 3000
+    u, i, y = O.synth_coo(nU, nI, nnz, seed=k)
+    st0 = O.initialize_parameters(nU, nI, k, 3, 0.3, 1.0, 0.3, 1.0, dtype)
+    ref = {k_: v.astype(np.float64) for k_, v in st0.items()}
+    for _ in range(2):
+        O.cavi_full_iteration(ref, y, u, i, **HYP)
+    out = _fit_gpu(y, u, i, nU, nI, k, 2, 3, dtype=dtype, chunk=32)
+    tol = 1e-11 if dtype == np.float64 else 2e-5
+    for key in STATE_KEYS:
+        assert relerr(out[key], ref[key]) < tol, key
+
+
+@pytest.mark.parametrize("sweep", [2, 3])
+@pytest.mark.parametrize("k,dtype", [(10, np.float64), (50, np.float32), (30, np.float32)])
+def test_alternative_sweeps_vs_oracle(golden_full, sweep, k, dtype):
+    """The one-pass (gather + RED) sweep and the cp.async.bulk/mbarrier staged-gather sweep compute the
+    same iteration as the default two-pass register-gather sweep."""
+    g = golden_full
+    st0 = O.initialize_parameters(100, 100, k, 123, 0.3, 1.0, 0.3, 1.0, dtype)
+    ref = {k_: v.astype(np.float64) for k_, v in st0.items()}
+    for _ in range(3):
+        O.cavi_full_iteration(ref, g["Y"], g["ix_u"], g["ix_i"], **HYP)
+    out = _fit_gpu(g["Y"], g["ix_u"], g["ix_i"], 100, 100, k, 3, 123, dtype=dtype, sweep=sweep, chunk=40)
+    tol = 1e-11 if dtype == np.float64 else 3e-5
+    for key in STATE_KEYS:
+        assert relerr(out[key], ref[key]) < tol, (key, sweep)
+
+
+def test_step_batch_ids_equals_explicit_batch(golden_full):
+    """Device-assembled minibatch (ids only) == caller-assembled minibatch (triples + unique lists),
+    for a user batch and an item batch, with and without blending all rates; also vs the oracle."""
+    g = golden_full
+    u, i, y = g["ix_u"], g["ix_i"], g["Y"]
+    st = O.initialize_parameters(100, 100, 10, 123, 0.3, 1.0, 0.3, 1.0)
+    for user_batch, ids in ((True, np.array([3, 50, 7, 99, 20, 21], np.int64)), (False, np.array([0, 98, 44, 45], np.int64))):
+        for blend_all in (False, True):
+            sel = np.isin(u, ids) if user_batch else np.isin(i, ids)
+            ub, ib, yb = u[sel], i[sel], y[sel]
+            users = ids if user_batch else np.unique(ub)
+            items = np.unique(ib) if user_batch else ids
+            e1 = _engine_from(st, 10, np.float64, panel_mb=1e9)
+            e1.load_coo(u, i, y)
+            e1.step_batch_ids(ids, user_batch, 0.6, 100.0 / ids.shape[0], blend_all)
+            a = e1.export_all()
+            e1.close()
+            e2 = _engine_from(st, 10, np.float64)
+            e2.step_batch(ub, ib, yb, np.ascontiguousarray(users), np.ascontiguousarray(items), user_batch, 0.6,
+                          100.0 / ids.shape[0], blend_all)
+            b = e2.export_all()
+            e2.close()
+            ref = {k_: v.copy() for k_, v in st.items()}
+            O._batch_step(ref, yb, ub, ib, np.sort(users), np.sort(items), user_batch, 0.6, 100.0 / ids.shape[0],
+                          0.3, 0.3, 0.3 + 10 * 0.3, 0.3 + 10 * 0.3, 0.3, 0.3, blend_all)
+            for key in STATE_KEYS:
+                assert relerr(a[key], b[key]) < 1e-12, (key, user_batch, blend_all)
+                assert relerr(a[key], ref[key]) < 1e-11, (key, user_batch, blend_all)
+    # ids-only batches need single-panel orderings
+    from hpfrec_b200 import _lib
+    e3 = _engine_from(st, 10, np.float64, panel_mb=0.001)
+    e3.load_coo(u, i, y)
+    with pytest.raises(_lib.HPFError):
+        e3.step_batch_ids(np.array([1, 2], np.int64), True, 0.5, 50.0, False)
+    e3.close()
+
+
+def test_fp32_svi_tracks_fp64(golden_svi):
+    """fp32 SVI (device-assembled batches) stays close to the fp64 reference run over 8 epochs."""
+    from hpfrec_b200.loops import cuda_loops_float as lp
+    g = golden_svi
+    Theta, Beta = np.empty((100, 10), np.float32), np.empty((100, 10), np.float32)
+    emp_r, emp_i = np.empty(0, np.float32), np.empty(0, dtype=np.uint64)
+    lp.fit_hpf(0.3, 0.3, 1.0, 0.3, 0.3, 1.0, g["Y"].astype(np.float32), g["ix_u"].astype(np.uint64),
+               g["ix_i"].astype(np.uint64), Theta, Beta, 8, "maxiter", 0, 1e-3, 20, 30, lambda x: 1 / np.sqrt(x + 2), 0,
+               g["st_ix_u"].astype(np.uint64), "", 123, 0, 1, 1, 0, emp_r, emp_i, emp_i, 0, 1, 0)
+    assert np.isfinite(Theta).all() and np.isfinite(Beta).all()
+    # different random start (float32 draws) => compare the fitted model, not the iterates: predicted
+    # counts of the training pairs correlate strongly with the fp64 fit's
+    pred32 = np.einsum("nk,nk->n", Theta[g["ix_u"]], Beta[g["ix_i"]])
+    pred64 = np.einsum("nk,nk->n", g["both_Theta"][g["ix_u"]], g["both_Beta"][g["ix_i"]])
+    assert np.corrcoef(pred32, pred64)[0, 1] > 0.8
