@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libhpf_b200_tune.so" if os.environ.get("HPF_TUNE") else "libhpf_b200.so")
+LIB_PATH = os.path.join(_HERE, "_lib", "libhpf_b200.so")
 
 # every symbol include/hpf_b200.h declares, with its argument types
 _c = ctypes

@@ -70,7 +70,7 @@ batch_prepare_kernel(int nrows, const int* __restrict__ rows, int ld, int k, con
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
         off[v] = (gl + LPG * v) * EPV;
-        act[v] = off[v] < ld;
+        act[v] = off[v] < k;
     }
     for (int q = g0; q < nrows; q += gstride) {
         // rows == nullptr: walk ALL rows and prepare those already stamped for this step (the unique
@@ -136,7 +136,7 @@ batch_major_kernel(int nrows, int ld, int k, const real* __restrict__ x, const r
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
         off[v] = (gl + LPG * v) * EPV;
-        act[v] = off[v] < ld;
+        act[v] = off[v] < k;
 #pragma unroll
         for (int e = 0; e < EPV; ++e) {
             other[v][e] = (act[v] && off[v] + e < k) ? (real)colsum_minor[off[v] + e] : real(0);
@@ -213,7 +213,7 @@ batch_minor_kernel(int nrows, const int* __restrict__ rows, int ld, int k, const
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
         off[v] = (gl + LPG * v) * EPV;
-        act[v] = off[v] < ld;
+        act[v] = off[v] < k;
 #pragma unroll
         for (int e = 0; e < EPV; ++e)
             other[v][e] = (act[v] && off[v] + e < k) ? (real)colsum_major[off[v] + e] : real(0);

@@ -65,6 +65,16 @@ __device__ __forceinline__ Pack<real> ldg_pack_hint(const real* p, uint64_t pol)
                  : "l"(p), "l"(pol));
     return r;
 }
+// gathered rows are touched once per SM: do not let them displace anything in L1
+template <typename real>
+__device__ __forceinline__ Pack<real> ldg_pack_noalloc(const real* p) {
+    Pack<real> r;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&r);
+    asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])
+                 : "l"(p));
+    return r;
+}
 __device__ __forceinline__ int ldg_stream(const int* p, uint64_t pol) {
     int v;
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));

@@ -47,6 +47,9 @@ int fail(int code, const char* fmt, ...) {
         if (rc_ != HPF_OK) return rc_; \
     } while (0)
 
+// default row alignment in bytes (see hpf_create); HPF_ROW_ALIGN overrides it
+constexpr int kDefaultRowAlign = 32;
+
 template <typename real_, int LPG, int VPL>
 struct Cfg {
     using real = real_;
@@ -177,6 +180,7 @@ struct hpf_engine {
     int device = 0;
     int64_t nU = 0, nI = 0;
     int k = 0, ld = 0, rb = 4;
+    int kw = 0;  // active row width: k rounded up to whole 16-byte packs (<= ld, the row stride)
     cudaStream_t stream = nullptr;
     // constants of the updates, already rounded to `real` the way the reference's typed locals are
     // (cdef real_t k_shp = a_prime + k*a, pxi:173-174; add_k_rte = a_prime/b_prime, pxi:209-210)
@@ -209,7 +213,8 @@ struct hpf_engine {
     int chunk = 64;
     int sweep_mode = 0;
     int use_graph = 0;
-    int v_lpg = 0, v_unroll = 0, v_minb = 0, v_hint = 0;  // sweep-kernel variant (tuning builds only)
+    int v_lpg = 0, v_minb = 0, v_hint = 0;  // sweep-kernel shape override (0 = default of the row class)
+    int strict = 0;                         // unknown shape = error instead of falling back to the default
     int64_t launches = 0;
     cudaGraphExec_t graph_lean = nullptr, graph_mat = nullptr;
     // optional per-kernel timing of full-batch iterations
@@ -411,7 +416,7 @@ int launch_sweep_variant(hpf_engine* h, const int* row, const int* col, const vo
     const long long threads = groups * LPG;
     hpf::sweep_major_kernel<real, LPG, VPL, UNROLL, MINB, HINT, FUSE><<<nblk(threads), 256, 0, h->stream>>>(
         row, col, (const real*)val, h->nnz, h->chunk, (const real*)xown, (const real*)xgat, (real*)acc,
-        (real*)acc_minor, h->ld);
+        (real*)acc_minor, h->ld, h->kw);
     h->launches++;
     CKK();
     return HPF_OK;
@@ -453,57 +458,62 @@ int launch_sweep_tma(hpf_engine* h, const int* row, const int* col, const void* 
     }
 }
 
-// Sweep-kernel shape.  The default (lane-group width, unroll, min blocks/SM, L2 hints) per row length
-// comes from measurements on B200 (profiles/); with -DHPF_TUNE every combination is compiled and the
-// "lpg"/"unroll"/"minb"/"hint" options select one at run time (tools/tune_sweep.py).
+// Sweep-kernel shape.  The default (lane-group width, min blocks/SM, load hints) per row-length class
+// comes from measurements on B200 (profiles/).  The candidate shapes of the fp32 classes stay compiled
+// in, and the "lpg" / "minb" / "hint" options select one at run time, so the tuners
+// (tools/tune_r2.py), the test-suite and bench.py all exercise the library that ships.  A shape that
+// does not exist for the row class at hand falls back to the default shape, unless option "strict" is
+// set (the tuners set it so that a typo cannot be timed as a result).
 template <typename C>
 int launch_sweep_major(hpf_engine* h, const int* row, const int* col, const void* val, const void* xown,
                        const void* xgat, void* acc, void* acc_minor = nullptr) {
     using real = typename C::real;
     if (h->nnz == 0) return HPF_OK;
-#ifdef HPF_TUNE
-    if (acc_minor != nullptr) {
-        constexpr int packs_f = C::lpg * C::vpl;
+    constexpr int packs = C::lpg * C::vpl;  // 16-byte packs per padded row handled by the default shape
+    if (acc_minor != nullptr && (h->v_lpg || h->v_minb || h->v_hint)) {
         const int lpg_f = h->v_lpg ? h->v_lpg : C::lpg, mb_f = h->v_minb ? h->v_minb : 3, hint_f = h->v_hint;
 #define HPF_F(L, M, H)                                  \
     if (lpg_f == L && mb_f == M && hint_f == H)         \
-        return launch_sweep_variant<real, L, packs_f / L, 1, M, H, 1>(h, row, col, val, xown, xgat, acc, acc_minor);
-        if constexpr (packs_f == 16 && sizeof(real) == 4) {
-            HPF_F(4, 3, 0) HPF_F(4, 3, 1) HPF_F(8, 3, 0) HPF_F(8, 3, 1) HPF_F(8, 4, 0) HPF_F(8, 4, 1) HPF_F(4, 2, 0) HPF_F(8, 2, 0)
+        return launch_sweep_variant<real, L, packs / L, 1, M, H, 1>(h, row, col, val, xown, xgat, acc, acc_minor);
+#define HPF_FL(L) HPF_F(L, 2, 0) HPF_F(L, 3, 0) HPF_F(L, 4, 0) HPF_F(L, 3, 1) HPF_F(L, 4, 1) HPF_F(L, 3, 3) HPF_F(L, 4, 3)
+        if constexpr (packs == 16 && sizeof(real) == 4) {
+            HPF_FL(4) HPF_FL(8) HPF_FL(16) HPF_F(8, 5, 0) HPF_F(8, 6, 0) HPF_F(16, 5, 0) HPF_F(16, 6, 0)
         }
+        if constexpr (packs == 8 && sizeof(real) == 4) {
+            HPF_F(4, 2, 0) HPF_F(4, 3, 0) HPF_F(4, 4, 0) HPF_F(8, 3, 0) HPF_F(8, 4, 0) HPF_F(8, 6, 0)
+        }
+        if constexpr (packs == 32 && sizeof(real) == 4) {
+            HPF_F(8, 2, 0) HPF_F(8, 3, 0) HPF_F(8, 4, 0) HPF_F(16, 2, 0) HPF_F(16, 3, 0) HPF_F(16, 4, 0) HPF_F(32, 2, 0) HPF_F(32, 4, 0)
+        }
+#undef HPF_FL
 #undef HPF_F
-        return fail(HPF_EINVAL, "no such fused sweep variant");
+        if (h->strict) return fail(HPF_EINVAL, "no such fused sweep variant (lpg=%d minb=%d hint=%d)", lpg_f, mb_f, hint_f);
     }
-#endif
-#ifdef HPF_TUNE
-    constexpr int packs = C::lpg * C::vpl;  // 16-byte packs per padded row handled by the default shape
-    const int lpg = h->v_lpg ? h->v_lpg : C::lpg, un = h->v_unroll ? h->v_unroll : 4;
-    const int mb = h->v_minb ? h->v_minb : 2, hint = h->v_hint;
-#define HPF_V(L, U, M, H)                                                          \
-    if (lpg == L && un == U && mb == M && hint == H)                               \
-        return launch_sweep_variant<real, L, packs / L, U, M, H>(h, row, col, val, xown, xgat, acc);
-#define HPF_VL(L)                                                                  \
-    HPF_V(L, 1, 2, 0) HPF_V(L, 2, 2, 0) HPF_V(L, 4, 2, 0) HPF_V(L, 1, 3, 0) HPF_V(L, 2, 3, 0) HPF_V(L, 4, 3, 0) \
-    HPF_V(L, 1, 4, 0) HPF_V(L, 2, 4, 0) HPF_V(L, 4, 4, 0) HPF_V(L, 1, 2, 1) HPF_V(L, 2, 2, 1) HPF_V(L, 4, 2, 1) \
-    HPF_V(L, 1, 3, 1) HPF_V(L, 2, 3, 1) HPF_V(L, 4, 3, 1) HPF_V(L, 1, 4, 1) HPF_V(L, 2, 4, 1) HPF_V(L, 4, 4, 1) \
-    HPF_V(L, 1, 2, 2) HPF_V(L, 1, 3, 2) HPF_V(L, 1, 4, 2)
-    if constexpr (packs == 16 && sizeof(real) == 4) {
-        HPF_VL(4) HPF_VL(8) HPF_VL(16)
-    }
-    if constexpr (packs == 8 && sizeof(real) == 4) {
-        HPF_VL(4) HPF_VL(8)
-    }
-    if constexpr (packs == 32 && sizeof(real) == 4) {
-        HPF_VL(8) HPF_VL(16) HPF_VL(32)
-    }
+    if (acc_minor == nullptr && (h->v_lpg || h->v_minb || h->v_hint)) {
+        const int lpg = h->v_lpg ? h->v_lpg : C::lpg, mb = h->v_minb ? h->v_minb : 3, hint = h->v_hint;
+#define HPF_V(L, M, H)                                  \
+    if (lpg == L && mb == M && hint == H)               \
+        return launch_sweep_variant<real, L, packs / L, 1, M, H>(h, row, col, val, xown, xgat, acc);
+#define HPF_VL(L) HPF_V(L, 2, 0) HPF_V(L, 3, 0) HPF_V(L, 4, 0) HPF_V(L, 2, 1) HPF_V(L, 3, 1) HPF_V(L, 4, 1) \
+                  HPF_V(L, 2, 3) HPF_V(L, 3, 3) HPF_V(L, 4, 3)
+        if constexpr (packs == 16 && sizeof(real) == 4) {
+            HPF_VL(4) HPF_VL(8) HPF_VL(16)
+            HPF_V(8, 5, 0) HPF_V(8, 6, 0) HPF_V(8, 5, 1) HPF_V(8, 6, 1) HPF_V(8, 5, 3) HPF_V(8, 6, 3)
+            HPF_V(16, 5, 0) HPF_V(16, 6, 0) HPF_V(16, 8, 0) HPF_V(16, 5, 3) HPF_V(16, 6, 3) HPF_V(16, 8, 3)
+        }
+        if constexpr (packs == 8 && sizeof(real) == 4) {
+            HPF_VL(4) HPF_VL(8)
+        }
+        if constexpr (packs == 32 && sizeof(real) == 4) {
+            HPF_VL(8) HPF_VL(16) HPF_VL(32)
+        }
 #undef HPF_VL
 #undef HPF_V
-    return fail(HPF_EINVAL, "no such sweep variant (lpg=%d unroll=%d minb=%d hint=%d)", lpg, un, mb, hint);
-#else
-    // Measured on B200 (profiles/r01_tune_*.jsonl, 1M x 380K x 48M nnz): narrow lane groups with no
-    // unrolling and 3-4 resident CTAs/SM beat wider groups / deeper unrolling at every row length.
-    constexpr int packs = C::lpg * C::vpl;
-    if (acc_minor != nullptr) {  // one-pass mode ("sweep"=2)
+        if (h->strict) return fail(HPF_EINVAL, "no such sweep variant (lpg=%d minb=%d hint=%d)", lpg, mb, hint);
+    }
+    // Shipped shapes, measured on B200 (profiles/r01_tune_*.jsonl, 1M x 380K x 48M nnz): narrow lane
+    // groups with no unrolling and 3-4 resident CTAs/SM beat wider groups / deeper unrolling.
+    if (acc_minor != nullptr) {  // one-pass modes ("sweep"=2, 4)
         if constexpr (packs <= 8) return launch_sweep_variant<real, 8, 1, 1, 3, 0, 1>(h, row, col, val, xown, xgat, acc, acc_minor);
         else if constexpr (packs <= 16) return launch_sweep_variant<real, 8, 2, 1, 3, 0, 1>(h, row, col, val, xown, xgat, acc, acc_minor);
         else return launch_sweep_variant<real, C::lpg, C::vpl, 1, 2, 0, 1>(h, row, col, val, xown, xgat, acc, acc_minor);
@@ -512,7 +522,6 @@ int launch_sweep_major(hpf_engine* h, const int* row, const int* col, const void
     else if constexpr (packs <= 16) return launch_sweep_variant<real, 4, 4, 1, 3, 1>(h, row, col, val, xown, xgat, acc);
     else if constexpr (packs <= 32) return launch_sweep_variant<real, 8, 4, 1, 4, 0>(h, row, col, val, xown, xgat, acc);
     else return launch_sweep_variant<real, C::lpg, C::vpl, 1, 2, 0>(h, row, col, val, xown, xgat, acc);
-#endif
 }
 
 template <typename C>
@@ -608,6 +617,17 @@ int do_sweep(hpf_engine* h, int sides = 3) {
     return dispatch(h->rb, h->ld, [&](auto cfg) {
         using C = decltype(cfg);
         if (sides & 1) mark(h, 0);
+        if (h->sweep_mode == 4) {
+            // one fused ITEM-major pass: item-side sums accumulate in registers (long segments, hot items
+            // cost nothing extra), every nnz pushes w * xi[i,:] into its user's sums with vector REDs
+            // (user degrees are small, so no address is hammered); both sides come out of the "item" call
+            if (sides & 1) {
+                TRY(launch_sweep_major<C>(h, h->B_row, h->B_col, h->B_val, h->xi, h->xu, h->accI, h->accU));
+                mark(h, 1);
+            }
+            if (sides & 2) mark(h, 2);
+            return HPF_OK;
+        }
         if (h->sweep_mode == 1 || h->sweep_mode == 2) {
             if (sides & 1) mark(h, 1);
             if (sides & 2) {
@@ -723,8 +743,27 @@ int hpf_create(hpf_engine** out, int64_t nU, int64_t nI, int32_t k, int32_t real
     }
     if (device < 0 || device >= ndev) return fail(HPF_EINVAL, "device %d out of range (%d devices)", device, ndev);
     DeviceGuard guard(device);
-    const int per32 = 32 / real_bytes;  // rows padded to whole 32-byte sectors
-    const int ld = (k + per32 - 1) / per32 * per32;
+    // Row stride: rows are padded so that every row starts on a boundary of `row_align` bytes.  32 = whole
+    // sectors (smallest footprint); 128 = whole cache lines, so a lane group's 128-byte load or RED never
+    // straddles two lines (fewer L1 tag look-ups and L2 requests per gathered row; measured in
+    // profiles/).  Pad packs beyond kw are never read or written by the sweep.
+    int row_align = kDefaultRowAlign;
+    if (const char* env = getenv("HPF_ROW_ALIGN")) row_align = atoi(env);
+    if (row_align != 32 && row_align != 64 && row_align != 128 && row_align != 256)
+        return fail(HPF_EINVAL, "HPF_ROW_ALIGN must be 32, 64, 128 or 256 (got %d)", row_align);
+    const int per_pack = 16 / real_bytes;
+    const int kw = (k + per_pack - 1) / per_pack * per_pack;
+    int ld = kw;
+    if ((size_t)kw * real_bytes > 32) {  // rows of one sector or less gain nothing from wider alignment
+        const int per_align = row_align / real_bytes;
+        // never pad a row to more than the next power of two of its size (a 36-byte row is not worth 128)
+        int cap = per_pack;
+        while (cap < kw) cap *= 2;
+        ld = (kw + per_align - 1) / per_align * per_align;
+        if (ld > cap) ld = cap;
+    }
+    const int per32 = 32 / real_bytes;  // at least whole 32-byte sectors
+    ld = (ld + per32 - 1) / per32 * per32;
     TRY(dispatch(real_bytes, ld, [](auto) { return HPF_OK; }));
     hpf_engine* h = new hpf_engine();
     h->device = device;
@@ -732,6 +771,7 @@ int hpf_create(hpf_engine** out, int64_t nU, int64_t nI, int32_t k, int32_t real
     h->nI = nI;
     h->k = k;
     h->ld = ld;
+    h->kw = kw;
     h->rb = real_bytes;
     hpf_set_hyper(h, 0.3, 0.3, 1.0, 0.3, 0.3, 1.0);  // the reference's defaults (hpfrec/__init__.py:205-206)
     const size_t mu = h->mat_bytes(nU > 0 ? nU : 1), mi = h->mat_bytes(nI > 0 ? nI : 1);
@@ -748,10 +788,41 @@ int hpf_create(hpf_engine** out, int64_t nU, int64_t nI, int32_t k, int32_t real
     if (e == cudaSuccess) e = hpf_malloc((void**)&h->Bsum, sizeof(double) * ld);
     if (e == cudaSuccess) e = cudaMemset(h->Tsum, 0, sizeof(double) * ld);
     if (e == cudaSuccess) e = cudaMemset(h->Bsum, 0, sizeof(double) * ld);
+    // pad packs of the factor buffers are skipped by the kernels: define them once
+    if (e == cudaSuccess) e = cudaMemsetAsync(h->xu, 0, mu, nullptr);
+    if (e == cudaSuccess) e = cudaMemsetAsync(h->xi, 0, mi, nullptr);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);  // the engine's stream may not be ordered after stream 0
     if (e != cudaSuccess) {
         int rc = fail(e == cudaErrorMemoryAllocation ? HPF_ENOMEM : HPF_ECUDA, "device allocation failed: %s", cudaGetErrorString(e));
         hpf_destroy(h);
         return rc;
+    }
+    // HPF_OPTIONS="name=value,name=value": defaults for hpf_set_option applied to every new engine (used by
+    // the tuning / measurement scripts to run the unmodified test-suite and bench under a candidate
+    // configuration).  Unknown names are an error.
+    if (const char* env = getenv("HPF_OPTIONS")) {
+        std::string all(env);
+        size_t pos = 0;
+        while (pos < all.size()) {
+            size_t end = all.find(',', pos);
+            if (end == std::string::npos) end = all.size();
+            const std::string item = all.substr(pos, end - pos);
+            pos = end + 1;
+            const size_t eq = item.find('=');
+            if (item.empty()) continue;
+            if (eq == std::string::npos) {
+                hpf_destroy(h);
+                return fail(HPF_EINVAL, "HPF_OPTIONS: expected name=value, got '%s'", item.c_str());
+            }
+            const std::string name = item.substr(0, eq);
+            const int rc = hpf_set_option(h, name.c_str(), atof(item.c_str() + eq + 1));
+            if (rc != HPF_OK) {
+                const std::string keep = g_err;
+                hpf_destroy(h);
+                g_err = keep;
+                return rc;
+            }
+        }
     }
     *out = h;
     return HPF_OK;
@@ -828,18 +899,19 @@ int hpf_set_option(hpf_engine* h, const char* name, double value) {
         h->chunk = (int)value;
         drop_graphs(h);
     } else if (!strcmp(name, "sweep")) {
+        if (value < 0 || value > 4) return fail(HPF_EINVAL, "sweep must be 0..4");
         h->sweep_mode = (int)value;
         drop_graphs(h);
-    } else if (!strcmp(name, "lpg") || !strcmp(name, "unroll") || !strcmp(name, "minb") || !strcmp(name, "hint")) {
-#ifndef HPF_TUNE
-        return fail(HPF_EINVAL, "option '%s' needs a library built with -DHPF_TUNE", name);
-#else
+    } else if (!strcmp(name, "lpg") || !strcmp(name, "minb") || !strcmp(name, "hint")) {
+        if (value < 0 || value > 64) return fail(HPF_EINVAL, "%s out of range", name);
         if (!strcmp(name, "lpg")) h->v_lpg = (int)value;
-        if (!strcmp(name, "unroll")) h->v_unroll = (int)value;
         if (!strcmp(name, "minb")) h->v_minb = (int)value;
         if (!strcmp(name, "hint")) h->v_hint = (int)value;
         drop_graphs(h);
-#endif
+    } else if (!strcmp(name, "unroll")) {
+        if (value != 0 && value != 1) return fail(HPF_EINVAL, "unrolled sweep shapes were measured slower and removed (unroll must be 1)");
+    } else if (!strcmp(name, "strict")) {
+        h->strict = (int)value;
     } else if (!strcmp(name, "use_graph")) {
         h->use_graph = (int)value;
     } else if (!strcmp(name, "timing")) {

@@ -23,6 +23,8 @@ namespace hpf {
 //     (row, chunk) segment, not once per nnz).
 //       acc[r, :] += sum_{n in segment} (Y[n] / dot(xown[r], xgat[c_n])) * xgat[c_n, :]
 // =============================================================================================
+//     HINT: 0 plain loads; 1 triples evict_first + gathers evict_last; 2 triples evict_first only;
+//     3 triples evict_first + gathers L1::no_allocate.
 //     FUSE=1 ("one-pass" mode): the same walk also pushes w_n * xown[r,:] into the MINOR side's sums
 //     with one vector RED per pack per nnz, so a single user-major pass produces both shape matrices;
 //     gathers ride the L2->SM response path and the REDs the SM->L2 request path.
@@ -31,7 +33,7 @@ __global__ void __launch_bounds__(256, MINB)
 sweep_major_kernel(const int* __restrict__ row, const int* __restrict__ col,
                    const real* __restrict__ val, long long nnz, int chunk,
                    const real* __restrict__ xown, const real* __restrict__ xgat,
-                   real* __restrict__ acc, real* __restrict__ acc_minor, int ld) {
+                   real* __restrict__ acc, real* __restrict__ acc_minor, int ld, int kw) {
     constexpr int EPV = Pack<real>::N;
     static_assert(LPG % UNROLL == 0, "UNROLL must divide LPG");
     const int gl = (threadIdx.x & 31) % LPG;
@@ -51,7 +53,7 @@ sweep_major_kernel(const int* __restrict__ row, const int* __restrict__ col,
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
         off[v] = (gl + LPG * v) * EPV;
-        act[v] = off[v] < ld;
+        act[v] = off[v] < kw;  // packs holding at least one real column (stride ld may be wider)
     }
     Pack<real> own[VPL], sum[VPL];
 #pragma unroll
@@ -107,6 +109,8 @@ sweep_major_kernel(const int* __restrict__ row, const int* __restrict__ col,
                 for (int v = 0; v < VPL; ++v) {
                     if (HINT == 1)
                         g[q][v] = act[v] ? ldg_pack_hint(src + off[v], pol_keep) : pack_zero<real>();
+                    else if (HINT == 3)
+                        g[q][v] = act[v] ? ldg_pack_noalloc(src + off[v]) : pack_zero<real>();
                     else
                         g[q][v] = act[v] ? ldg_pack(src + off[v]) : pack_zero<real>();
                 }
@@ -184,7 +188,7 @@ sweep_coo_kernel(const int* __restrict__ iu, const int* __restrict__ ii, const r
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
         off[v] = (gl + LPG * v) * EPV;
-        act[v] = off[v] < ld;
+        act[v] = off[v] < k;
     }
     for (long long base = beg; base < end; base += LPG) {
         const long long idx = base + gl;
@@ -268,7 +272,7 @@ update_rows_kernel(int nrows, int ld, int k, real* __restrict__ x, real* __restr
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
         off[v] = (gl + LPG * v) * EPV;
-        act[v] = off[v] < ld;
+        act[v] = off[v] < k;
 #pragma unroll
         for (int e = 0; e < EPV; ++e) {
             const int j = off[v] + e;
@@ -373,7 +377,7 @@ update_items_peer_kernel(int r0, int r1, int ld, int k, PeerTable pt, const doub
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
         off[v] = (gl + LPG * v) * EPV;
-        act[v] = off[v] < ld;
+        act[v] = off[v] < k;
 #pragma unroll
         for (int e = 0; e < EPV; ++e) {
             const int j = off[v] + e;
@@ -485,7 +489,7 @@ rows_to_x_kernel(int nrows, const int* __restrict__ rows, int ld, int k, const r
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
         off[v] = (gl + LPG * v) * EPV;
-        act[v] = off[v] < ld;
+        act[v] = off[v] < k;
 #pragma unroll
         for (int e = 0; e < EPV; ++e) csum[v][e] = real(0);
     }

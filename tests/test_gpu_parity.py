@@ -323,11 +323,12 @@ def test_wide_rows_vs_oracle(k, dtype):
         assert relerr(out[key], ref[key]) < tol, key
 
 
-@pytest.mark.parametrize("sweep", [2, 3])
-@pytest.mark.parametrize("k,dtype", [(10, np.float64), (50, np.float32), (30, np.float32)])
+@pytest.mark.parametrize("sweep", [2, 3, 4])
+@pytest.mark.parametrize("k,dtype", [(10, np.float64), (50, np.float32), (30, np.float32), (128, np.float32)])
 def test_alternative_sweeps_vs_oracle(golden_full, sweep, k, dtype):
-    """The one-pass (gather + RED) sweep and the cp.async.bulk/mbarrier staged-gather sweep compute the
-    same iteration as the default two-pass register-gather sweep."""
+    """The one-pass (gather + RED) sweeps (2: user-major walk, 4: item-major walk) and the
+    cp.async.bulk/mbarrier staged-gather sweep (3) compute the same iteration as the default two-pass
+    register-gather sweep."""
     g = golden_full
     st0 = O.initialize_parameters(100, 100, k, 123, 0.3, 1.0, 0.3, 1.0, dtype)
     ref = {k_: v.astype(np.float64) for k_, v in st0.items()}
@@ -391,3 +392,71 @@ def test_fp32_svi_tracks_fp64(golden_svi):
     pred32 = np.einsum("nk,nk->n", Theta[g["ix_u"]], Beta[g["ix_i"]])
     pred64 = np.einsum("nk,nk->n", g["both_Theta"][g["ix_u"]], g["both_Beta"][g["ix_i"]])
     assert np.corrcoef(pred32, pred64)[0, 1] > 0.8
+
+
+def _expected_ld(k, itemsize, align):
+    """Row stride rule of hpf_create: k rounded up to 16-byte packs, then to `align` bytes but never
+    beyond the next power of two of the row, then to whole 32-byte sectors."""
+    pack = 16 // itemsize
+    kw = -(-k // pack) * pack
+    ld = kw
+    if kw * itemsize > 32:
+        per, cap = align // itemsize, pack
+        while cap < kw:
+            cap *= 2
+        ld = min(-(-kw // per) * per, cap)
+    per32 = 32 // itemsize
+    return -(-ld // per32) * per32
+
+
+@pytest.mark.parametrize("align", [32, 64, 128, 256])
+@pytest.mark.parametrize("k,dtype,ld32", [(50, np.float32, 56), (10, np.float64, 12), (7, np.float64, 8),
+                                          (30, np.float32, 32), (70, np.float32, 72), (3, np.float32, 8)])
+def test_row_alignment_is_result_neutral(monkeypatch, golden_full, align, k, dtype, ld32):
+    """HPF_ROW_ALIGN only changes the row stride of the device matrices (32 B = whole sectors, 128 B =
+    whole cache lines): the stride follows the documented rule and every sweep implementation returns
+    the same iteration as the oracle."""
+    from hpfrec_b200.engine import Engine
+    monkeypatch.setenv("HPF_ROW_ALIGN", str(align))
+    probe = Engine(5, 5, k, np.dtype(dtype).itemsize)
+    ld = probe.ld
+    probe.close()
+    assert ld == _expected_ld(k, np.dtype(dtype).itemsize, align)
+    if align == 32:
+        assert ld == ld32   # whole sectors: the layout of DESIGN.md section 4
+    g = golden_full
+    st0 = O.initialize_parameters(100, 100, k, 123, 0.3, 1.0, 0.3, 1.0, dtype)
+    ref = {k_: v.astype(np.float64) for k_, v in st0.items()}
+    for _ in range(3):
+        O.cavi_full_iteration(ref, g["Y"], g["ix_u"], g["ix_i"], **HYP)
+    tol = 1e-11 if dtype == np.float64 else 3e-5
+    for sweep in (0, 1, 2, 4):
+        out = _fit_gpu(g["Y"], g["ix_u"], g["ix_i"], 100, 100, k, 3, 123, dtype=dtype, sweep=sweep, chunk=24,
+                       panel_mb=0.004)
+        for key in STATE_KEYS:
+            assert relerr(out[key], ref[key]) < tol, (key, sweep, align)
+
+
+def test_row_alignment_minibatch_and_metrics(monkeypatch, golden_full, golden_pf):
+    """The minibatch step, llk and predict kernels with cache-line-aligned rows (stride != active width)."""
+    monkeypatch.setenv("HPF_ROW_ALIGN", "128")
+    test_partial_fit_vs_golden_reference(golden_full, golden_pf)
+    test_llk_and_predict_vs_golden_reference(golden_full)
+    test_step_batch_ids_equals_explicit_batch(golden_full)
+
+
+def test_engine_options_from_environment(monkeypatch, golden_full):
+    """HPF_OPTIONS applies hpf_set_option defaults to every new engine; unknown names fail loudly."""
+    from hpfrec_b200 import _lib
+    from hpfrec_b200.engine import Engine
+    g = golden_full
+    monkeypatch.setenv("HPF_OPTIONS", "sweep=4,chunk=32,panel_mb=0.01")
+    out = _fit_gpu(g["Y"], g["ix_u"], g["ix_i"], 100, 100, 10, 10, 123)
+    for key in STATE_KEYS:
+        assert relerr(out[key], g["it10_%s" % key]) < 1e-11, key
+    monkeypatch.setenv("HPF_OPTIONS", "no_such_option=1")
+    with pytest.raises(_lib.HPFError):
+        Engine(5, 5, 4, 8)
+    monkeypatch.setenv("HPF_OPTIONS", "sweep")
+    with pytest.raises(_lib.HPFError):
+        Engine(5, 5, 4, 8)

@@ -1,9 +1,9 @@
 #!/usr/bin/env python3
-"""DRAM traffic / L2 hit rate of the sweep kernel vs panel size and L2 hint (tuning build, GPU box)."""
+"""DRAM traffic / L2 hit rate of the sweep kernel vs panel size and L2 hint (GPU box)."""
 import csv, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 os.chdir(ROOT)
-env = dict(os.environ, HPF_TUNE="1")
+env = dict(os.environ)
 METRICS = "dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,gpu__time_duration.sum"
 panels = [float(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else "12,24,32,48,96".split(","))]
 for P in panels:

@@ -1,6 +1,5 @@
 #!/bin/bash
-# DRAM traffic / L2 hit rate of the sweep kernel vs panel size (tuning build).  Run on the GPU box.
-export HPF_TUNE=1
+# DRAM traffic / L2 hit rate of the sweep kernel vs panel size.  Run on the GPU box.
 for P in 12 24 32 48 96; do
   for H in 0 1; do
     ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,gpu__time_duration.sum \

@@ -1,8 +1,7 @@
 #!/usr/bin/env python3
-"""One-pass (fused gather + RED) sweep vs two-pass sweep, tuning build, GPU box.
-HPF_TUNE=1 python tools/tune_fused.py [--alpha 0.6]"""
+"""One-pass (fused gather + RED) sweep vs two-pass sweep, GPU box.
+python tools/tune_fused.py [--alpha 0.6]"""
 import argparse, json, os, sys
-os.environ.setdefault("HPF_TUNE", "1")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np, torch, bench

@@ -1,7 +1,6 @@
 #!/usr/bin/env python3
-"""Staged-gather (cp.async.bulk) sweep vs register-gather sweep: agreement + timing (tuning build)."""
+"""Staged-gather (cp.async.bulk) sweep vs register-gather sweep: agreement + timing."""
 import argparse, json, os, sys
-os.environ.setdefault("HPF_TUNE", "1")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np, torch, bench
