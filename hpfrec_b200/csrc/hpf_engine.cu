@@ -47,8 +47,26 @@ int fail(int code, const char* fmt, ...) {
         if (rc_ != HPF_OK) return rc_; \
     } while (0)
 
-// default row alignment in bytes (see hpf_create); HPF_ROW_ALIGN overrides it
-constexpr int kDefaultRowAlign = 32;
+// -------------------------------------------------------------------------------------------------
+// Measured defaults (B200, 1M x 380K x 48M nnz; profiles/).  Everything a tuning run can change lives
+// in this block; each value is also an option (hpf_set_option / HPF_OPTIONS / HPF_ROW_ALIGN), so the
+// test-suite and the bench can be run under a candidate configuration before it becomes the default.
+// -------------------------------------------------------------------------------------------------
+constexpr int kDefaultRowAlign = 32;     // bytes; row stride rule in hpf_create
+constexpr double kDefaultPanelMb = 48.0;  // L2 panel of the gathered factor side
+constexpr int kDefaultChunk = 64;        // nnz walked by one lane group
+constexpr int kDefaultSweepMode = 0;     // 0 two-pass, 2 fused user-major, 4 fused item-major
+
+struct Shape {
+    int lpg, minb, hint;  // lanes per row, resident CTAs per SM (launch bound), load hints (see sweep_major_kernel)
+};
+// fp32 row classes by capacity in 16-byte packs (8: k<=32, 16: k<=64, 32: k<=128); {0,0,0} = generic shape
+inline Shape default_shape(int packs, int real_bytes, bool fused) {
+    if (real_bytes == 4 && packs == 8) return fused ? Shape{8, 3, 0} : Shape{4, 2, 0};
+    if (real_bytes == 4 && packs == 16) return fused ? Shape{8, 3, 0} : Shape{4, 3, 1};
+    if (real_bytes == 4 && packs == 32) return fused ? Shape{16, 2, 0} : Shape{8, 4, 0};
+    return Shape{0, 0, 0};
+}
 
 template <typename real_, int LPG, int VPL>
 struct Cfg {
@@ -209,11 +227,11 @@ struct hpf_engine {
     size_t bt_scan_bytes = 0;
     int64_t bt_cap_nnz = 0, bt_cap_ids = 0;
     // options
-    double panel_mb = 48.0;
-    int chunk = 64;
-    int sweep_mode = 0;
+    double panel_mb = kDefaultPanelMb;
+    int chunk = kDefaultChunk;
+    int sweep_mode = kDefaultSweepMode;
     int use_graph = 0;
-    int v_lpg = 0, v_minb = 0, v_hint = 0;  // sweep-kernel shape override (0 = default of the row class)
+    int v_lpg = 0, v_minb = 0, v_hint = -1;  // sweep-kernel shape overrides (0 / -1 = default of the row class)
     int strict = 0;                         // unknown shape = error instead of falling back to the default
     int64_t launches = 0;
     cudaGraphExec_t graph_lean = nullptr, graph_mat = nullptr;
@@ -469,11 +487,15 @@ int launch_sweep_major(hpf_engine* h, const int* row, const int* col, const void
                        const void* xgat, void* acc, void* acc_minor = nullptr) {
     using real = typename C::real;
     if (h->nnz == 0) return HPF_OK;
-    constexpr int packs = C::lpg * C::vpl;  // 16-byte packs per padded row handled by the default shape
-    if (acc_minor != nullptr && (h->v_lpg || h->v_minb || h->v_hint)) {
-        const int lpg_f = h->v_lpg ? h->v_lpg : C::lpg, mb_f = h->v_minb ? h->v_minb : 3, hint_f = h->v_hint;
-#define HPF_F(L, M, H)                                  \
-    if (lpg_f == L && mb_f == M && hint_f == H)         \
+    constexpr int packs = C::lpg * C::vpl;  // capacity of the row class in 16-byte packs
+    const bool fused = acc_minor != nullptr;
+    // shape = measured default of the class, overridden field by field by the options
+    const Shape def = default_shape(packs, (int)sizeof(real), fused);
+    const int lpg = h->v_lpg ? h->v_lpg : def.lpg, mb = h->v_minb ? h->v_minb : def.minb;
+    const int hint = h->v_hint >= 0 ? h->v_hint : def.hint;
+    if (fused) {
+#define HPF_F(L, M, H)                          \
+    if (lpg == L && mb == M && hint == H)       \
         return launch_sweep_variant<real, L, packs / L, 1, M, H, 1>(h, row, col, val, xown, xgat, acc, acc_minor);
 #define HPF_FL(L) HPF_F(L, 2, 0) HPF_F(L, 3, 0) HPF_F(L, 4, 0) HPF_F(L, 3, 1) HPF_F(L, 4, 1) HPF_F(L, 3, 3) HPF_F(L, 4, 3)
         if constexpr (packs == 16 && sizeof(real) == 4) {
@@ -487,12 +509,9 @@ int launch_sweep_major(hpf_engine* h, const int* row, const int* col, const void
         }
 #undef HPF_FL
 #undef HPF_F
-        if (h->strict) return fail(HPF_EINVAL, "no such fused sweep variant (lpg=%d minb=%d hint=%d)", lpg_f, mb_f, hint_f);
-    }
-    if (acc_minor == nullptr && (h->v_lpg || h->v_minb || h->v_hint)) {
-        const int lpg = h->v_lpg ? h->v_lpg : C::lpg, mb = h->v_minb ? h->v_minb : 3, hint = h->v_hint;
-#define HPF_V(L, M, H)                                  \
-    if (lpg == L && mb == M && hint == H)               \
+    } else {
+#define HPF_V(L, M, H)                          \
+    if (lpg == L && mb == M && hint == H)       \
         return launch_sweep_variant<real, L, packs / L, 1, M, H>(h, row, col, val, xown, xgat, acc);
 #define HPF_VL(L) HPF_V(L, 2, 0) HPF_V(L, 3, 0) HPF_V(L, 4, 0) HPF_V(L, 2, 1) HPF_V(L, 3, 1) HPF_V(L, 4, 1) \
                   HPF_V(L, 2, 3) HPF_V(L, 3, 3) HPF_V(L, 4, 3)
@@ -509,13 +528,13 @@ int launch_sweep_major(hpf_engine* h, const int* row, const int* col, const void
         }
 #undef HPF_VL
 #undef HPF_V
-        if (h->strict) return fail(HPF_EINVAL, "no such sweep variant (lpg=%d minb=%d hint=%d)", lpg, mb, hint);
     }
-    // Shipped shapes, measured on B200 (profiles/r01_tune_*.jsonl, 1M x 380K x 48M nnz): narrow lane
-    // groups with no unrolling and 3-4 resident CTAs/SM beat wider groups / deeper unrolling.
-    if (acc_minor != nullptr) {  // one-pass modes ("sweep"=2, 4)
-        if constexpr (packs <= 8) return launch_sweep_variant<real, 8, 1, 1, 3, 0, 1>(h, row, col, val, xown, xgat, acc, acc_minor);
-        else if constexpr (packs <= 16) return launch_sweep_variant<real, 8, 2, 1, 3, 0, 1>(h, row, col, val, xown, xgat, acc, acc_minor);
+    if (h->strict && (h->v_lpg || h->v_minb || h->v_hint >= 0))
+        return fail(HPF_EINVAL, "no such %s sweep shape for this row class (lpg=%d minb=%d hint=%d)",
+                    fused ? "fused" : "two-pass", lpg, mb, hint);
+    // generic shape of the classes without a measured table entry (fp64, rows beyond 512 bytes)
+    if (fused) {
+        if constexpr (packs <= 16) return launch_sweep_variant<real, 8, packs / 8, 1, 3, 0, 1>(h, row, col, val, xown, xgat, acc, acc_minor);
         else return launch_sweep_variant<real, C::lpg, C::vpl, 1, 2, 0, 1>(h, row, col, val, xown, xgat, acc, acc_minor);
     }
     if constexpr (packs <= 8) return launch_sweep_variant<real, 4, 2, 1, 2, 0>(h, row, col, val, xown, xgat, acc);
@@ -903,10 +922,10 @@ int hpf_set_option(hpf_engine* h, const char* name, double value) {
         h->sweep_mode = (int)value;
         drop_graphs(h);
     } else if (!strcmp(name, "lpg") || !strcmp(name, "minb") || !strcmp(name, "hint")) {
-        if (value < 0 || value > 64) return fail(HPF_EINVAL, "%s out of range", name);
-        if (!strcmp(name, "lpg")) h->v_lpg = (int)value;
-        if (!strcmp(name, "minb")) h->v_minb = (int)value;
-        if (!strcmp(name, "hint")) h->v_hint = (int)value;
+        if (value < -1 || value > 64) return fail(HPF_EINVAL, "%s out of range", name);
+        if (!strcmp(name, "lpg")) h->v_lpg = value > 0 ? (int)value : 0;      // 0 = default of the row class
+        if (!strcmp(name, "minb")) h->v_minb = value > 0 ? (int)value : 0;    // 0 = default
+        if (!strcmp(name, "hint")) h->v_hint = (int)value;                    // -1 = default
         drop_graphs(h);
     } else if (!strcmp(name, "unroll")) {
         if (value != 0 && value != 1) return fail(HPF_EINVAL, "unrolled sweep shapes were measured slower and removed (unroll must be 1)");

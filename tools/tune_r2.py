@@ -160,10 +160,11 @@ def main():
         if idx > 1 and spent() > a.budget_s * 0.55:
             print("budget: skipping", align, panel, flush=True)
             continue
-        if (align, panel) == (32, 48.0):
-            setup = s0
-        else:
-            setup = Setup(50, 0.6, align, panel)
+        try:
+            setup = s0 if (align, panel) == (32, 48.0) else Setup(50, 0.6, align, panel)
+        except Exception as exc:  # e.g. out of memory: keep what we have
+            print("setup failed", align, panel, repr(exc)[:200], flush=True)
+            continue
         sweep_setup(setup, (0, 2, 4), 0, ref)
         if setup is not s0:
             setup.close()
@@ -184,7 +185,11 @@ def main():
     for align, panel in seen:
         if spent() > a.budget_s * 0.8:
             break
-        setup = s0 if (align, panel) == (32, 48.0) else Setup(50, 0.6, align, panel)
+        try:
+            setup = s0 if (align, panel) == (32, 48.0) else Setup(50, 0.6, align, panel)
+        except Exception as exc:
+            print("setup failed", align, panel, repr(exc)[:200], flush=True)
+            continue
         modes = sorted({r["sweep"] for r in good[:6]} | {0})
         sweep_setup(setup, modes, 1, ref)
         if setup is not s0:
