@@ -67,6 +67,14 @@ inline Shape default_shape(int packs, int real_bytes, bool fused) {
     if (real_bytes == 4 && packs == 32) return fused ? Shape{16, 2, 0} : Shape{8, 4, 0};
     return Shape{0, 0, 0};
 }
+// shapes of the pipelined two-pass kernel (option "kernel"=2)
+inline Shape default_shape_v2(int packs, int real_bytes) {
+    if (real_bytes == 4 && packs == 8) return Shape{8, 6, 0};
+    if (real_bytes == 4 && packs == 16) return Shape{8, 3, 0};
+    if (real_bytes == 4 && packs == 32) return Shape{16, 3, 0};
+    return Shape{0, 0, 0};
+}
+constexpr int kDefaultKernel = 1;  // 1 = sweep_major_kernel, 2 = sweep_major_v2_kernel (two-pass mode only)
 
 template <typename real_, int LPG, int VPL>
 struct Cfg {
@@ -233,6 +241,7 @@ struct hpf_engine {
     int use_graph = 0;
     int v_lpg = 0, v_minb = 0, v_hint = -1;  // sweep-kernel shape overrides (0 / -1 = default of the row class)
     int strict = 0;                         // unknown shape = error instead of falling back to the default
+    int kernel_ver = kDefaultKernel;        // two-pass sweep kernel: 1 classic, 2 pipelined
     int64_t launches = 0;
     cudaGraphExec_t graph_lean = nullptr, graph_mat = nullptr;
     // optional per-kernel timing of full-batch iterations
@@ -440,6 +449,18 @@ int launch_sweep_variant(hpf_engine* h, const int* row, const int* col, const vo
     return HPF_OK;
 }
 
+template <typename real, int LPG, int VPL, int MINB, int HINT>
+int launch_sweep_v2(hpf_engine* h, const int* row, const int* col, const void* val, const void* xown,
+                    const void* xgat, void* acc) {
+    const long long groups = (h->nnz + h->chunk - 1) / h->chunk;
+    const long long threads = groups * LPG;
+    hpf::sweep_major_v2_kernel<real, LPG, VPL, MINB, HINT><<<nblk(threads), 256, 0, h->stream>>>(
+        row, col, (const real*)val, h->nnz, h->chunk, (const real*)xown, (const real*)xgat, (real*)acc, h->ld, h->kw);
+    h->launches++;
+    CKK();
+    return HPF_OK;
+}
+
 // staged-gather sweep (hpf_sweep_tma.cuh): 8 lanes per row, rows staged in shared memory by bulk copies
 template <typename real, int VPL, int MINB>
 int launch_sweep_tma_variant(hpf_engine* h, const int* row, const int* col, const void* val, const void* xown,
@@ -493,6 +514,32 @@ int launch_sweep_major(hpf_engine* h, const int* row, const int* col, const void
     const Shape def = default_shape(packs, (int)sizeof(real), fused);
     const int lpg = h->v_lpg ? h->v_lpg : def.lpg, mb = h->v_minb ? h->v_minb : def.minb;
     const int hint = h->v_hint >= 0 ? h->v_hint : def.hint;
+    if (!fused && h->kernel_ver == 2) {  // pipelined two-pass kernel (sweep_major_v2_kernel)
+        const Shape d2 = default_shape_v2(packs, (int)sizeof(real));
+        const int l2 = h->v_lpg ? h->v_lpg : d2.lpg, m2 = h->v_minb ? h->v_minb : d2.minb;
+        const int h2 = h->v_hint >= 0 ? h->v_hint : d2.hint;
+#define HPF_P(L, M, H)                          \
+    if (l2 == L && m2 == M && h2 == H)          \
+        return launch_sweep_v2<real, L, packs / L, M, H>(h, row, col, val, xown, xgat, acc);
+#define HPF_PL(L) HPF_P(L, 2, 0) HPF_P(L, 3, 0) HPF_P(L, 4, 0) HPF_P(L, 5, 0) HPF_P(L, 6, 0) \
+                  HPF_P(L, 2, 1) HPF_P(L, 3, 1) HPF_P(L, 4, 1) HPF_P(L, 5, 1) HPF_P(L, 6, 1)
+        if constexpr (packs == 16 && sizeof(real) == 4) {
+            HPF_PL(4) HPF_PL(8) HPF_PL(16)
+        }
+        if constexpr (packs == 8 && sizeof(real) == 4) {
+            HPF_P(4, 3, 0) HPF_P(4, 4, 0) HPF_P(4, 6, 0) HPF_P(8, 4, 0) HPF_P(8, 6, 0) HPF_P(8, 8, 0)
+        }
+        if constexpr (packs == 32 && sizeof(real) == 4) {
+            HPF_P(8, 2, 0) HPF_P(8, 3, 0) HPF_P(16, 2, 0) HPF_P(16, 3, 0) HPF_P(16, 4, 0) HPF_P(32, 3, 0) HPF_P(32, 4, 0)
+        }
+#undef HPF_PL
+#undef HPF_P
+        if (h->strict && (h->v_lpg || h->v_minb || h->v_hint >= 0))
+            return fail(HPF_EINVAL, "no such pipelined sweep shape for this row class (lpg=%d minb=%d hint=%d)", l2, m2, h2);
+        // generic shape (fp64, rows beyond 512 bytes)
+        if constexpr (packs <= 16) return launch_sweep_v2<real, 8, packs / 8, 3, 0>(h, row, col, val, xown, xgat, acc);
+        else return launch_sweep_v2<real, C::lpg, C::vpl, 2, 0>(h, row, col, val, xown, xgat, acc);
+    }
     if (fused) {
 #define HPF_F(L, M, H)                          \
     if (lpg == L && mb == M && hint == H)       \
@@ -929,6 +976,10 @@ int hpf_set_option(hpf_engine* h, const char* name, double value) {
         drop_graphs(h);
     } else if (!strcmp(name, "unroll")) {
         if (value != 0 && value != 1) return fail(HPF_EINVAL, "unrolled sweep shapes were measured slower and removed (unroll must be 1)");
+    } else if (!strcmp(name, "kernel")) {
+        if (value != 1 && value != 2) return fail(HPF_EINVAL, "kernel must be 1 (classic) or 2 (pipelined)");
+        h->kernel_ver = (int)value;
+        drop_graphs(h);
     } else if (!strcmp(name, "strict")) {
         h->strict = (int)value;
     } else if (!strcmp(name, "use_graph")) {

@@ -166,6 +166,191 @@ sweep_major_kernel(const int* __restrict__ row, const int* __restrict__ col,
 }
 
 // =============================================================================================
+// K2 (pipelined form) -- same contract as sweep_major_kernel without FUSE:
+//       acc[r, :] += sum_{n in segment} (Y[n] / dot(xown[r], xgat[c_n])) * xgat[c_n, :]
+// The probe of the bare access pattern (tools/gather_probe.cu, profiles/r01b_gather_probe_*.jsonl) moves
+// 48M random 208-byte rows out of a 48 MB L2 window in 0.58-0.60 ms, while the kernel above needs
+// 1.5 ms for the same gathers: every step serialises  shuffle -> gather -> dot -> butterfly -> divide ->
+// FMA, so a warp waits one full L2 round trip PLUS the dependent arithmetic per nnz, and lane-group
+// masked shuffles cost a MATCH/REDUX/VOTE/branch sequence each.  This form
+//   * keeps control flow uniform across the WARP (every group runs the same number of steps; steps past
+//     the end of a group's chunk are predicated off), so all shuffles use the full mask and compile to
+//     bare SHFL;
+//   * software-pipelines one step ahead: while step t is reduced and accumulated, the gathered row of
+//     step t+1 -- and, when the major id changes at t+1, the group's own row -- are already in flight.
+// =============================================================================================
+template <typename real, int LPG, int VPL, int MINB, int HINT>
+__global__ void __launch_bounds__(256, MINB)
+sweep_major_v2_kernel(const int* __restrict__ row, const int* __restrict__ col, const real* __restrict__ val,
+                      long long nnz, int chunk, const real* __restrict__ xown, const real* __restrict__ xgat,
+                      real* __restrict__ acc, int ld, int kw) {
+    constexpr int EPV = Pack<real>::N;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % LPG;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // warp-uniform exit: the first group of this warp already starts past the end
+    if (((tid - lane) / LPG) * (long long)chunk >= nnz) return;
+    const long long group = tid / LPG;
+    long long beg = group * (long long)chunk;
+    if (beg > nnz) beg = nnz;  // later groups of the last warp stay alive with an empty range
+    const long long end = (beg + chunk < nnz) ? beg + chunk : nnz;
+    const int nbatch = (chunk + LPG - 1) / LPG;  // identical for every group of the grid
+
+    uint64_t pol_keep = 0, pol_stream = 0;
+    if (HINT) {
+        pol_keep = l2_policy_keep();
+        pol_stream = l2_policy_stream();
+    }
+    const unsigned row_bytes = (unsigned)ld * (unsigned)sizeof(real);
+    const char* gat_base = reinterpret_cast<const char*>(xgat);
+    const char* own_base = reinterpret_cast<const char*>(xown);
+    unsigned offb[VPL];  // byte offset of this lane's packs inside a row
+    bool act[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        offb[v] = (unsigned)((gl + LPG * v) * EPV) * (unsigned)sizeof(real);
+        act[v] = (gl + LPG * v) * EPV < kw;
+    }
+
+    auto load_triple = [&](long long idx, int& r, int& c, real& y) {
+        r = -1;
+        c = 0;
+        y = real(0);
+        if (idx < end) {
+            if (HINT) {
+                r = ldg_stream(row + idx, pol_stream);
+                c = ldg_stream(col + idx, pol_stream);
+                y = ldg_stream(val + idx, pol_stream);
+            } else {
+                r = __ldg(row + idx);
+                c = __ldg(col + idx);
+                y = __ldg(val + idx);
+            }
+        }
+    };
+    auto gather = [&](int cc, bool valid, Pack<real>(&g)[VPL]) {
+        const char* src = gat_base + (uint64_t)(unsigned)cc * row_bytes;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            if (valid && act[v]) {
+                if (HINT == 1)
+                    g[v] = ldg_pack_hint(reinterpret_cast<const real*>(src + offb[v]), pol_keep);
+                else
+                    g[v] = ldg_pack(reinterpret_cast<const real*>(src + offb[v]));
+            } else {
+                g[v] = pack_zero<real>();
+            }
+        }
+    };
+
+    Pack<real> own[VPL], own_nx[VPL], sum[VPL], g_nx[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        own[v] = pack_zero<real>();
+        own_nx[v] = pack_zero<real>();
+        sum[v] = pack_zero<real>();
+    }
+    int cur = -1;
+
+    // batch 0 and the pipeline prologue (step 0 of batch 0)
+    int r, c;
+    real y;
+    load_triple(beg + gl, r, c, y);
+    int r_st = __shfl_sync(FULL, r, 0, LPG);
+    real y_st = __shfl_sync(FULL, y, 0, LPG);
+    {
+        const int c0 = __shfl_sync(FULL, c, 0, LPG);
+        gather(c0, r_st >= 0, g_nx);
+    }
+    bool chg_st = r_st >= 0;  // cur == -1: the first valid nnz always opens a row
+    if (chg_st) {
+        const char* src = own_base + (uint64_t)(unsigned)r_st * row_bytes;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+            if (act[v]) own_nx[v] = ldg_pack(reinterpret_cast<const real*>(src + offb[v]));
+    }
+
+    for (int b = 0; b < nbatch; ++b) {
+        int rn, cn;
+        real yn;
+        load_triple((b + 1 < nbatch) ? beg + (long long)(b + 1) * LPG + gl : end, rn, cn, yn);
+#pragma unroll
+        for (int t = 0; t < LPG; ++t) {
+            // ---- this step's operands were fetched one step ago
+            Pack<real> g[VPL];
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) g[v] = g_nx[v];
+            const int rr = r_st;
+            const real yy = y_st;
+            const bool valid = rr >= 0;
+            if (chg_st) {  // divergent between groups, no shuffles inside
+                if (cur >= 0) {
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v)
+                        if (act[v]) red_add_pack(acc + (size_t)cur * ld + (gl + LPG * v) * EPV, sum[v]);
+                }
+                cur = rr;
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) {
+                    own[v] = own_nx[v];
+                    sum[v] = pack_zero<real>();
+                }
+            }
+            // ---- put the next step in flight (warp-uniform shuffles)
+            int c2, r2;
+            real y2;
+            if (t + 1 < LPG) {
+                c2 = __shfl_sync(FULL, c, t + 1, LPG);
+                r2 = __shfl_sync(FULL, r, t + 1, LPG);
+                y2 = __shfl_sync(FULL, y, t + 1, LPG);
+            } else {
+                c2 = __shfl_sync(FULL, cn, 0, LPG);
+                r2 = __shfl_sync(FULL, rn, 0, LPG);
+                y2 = __shfl_sync(FULL, yn, 0, LPG);
+            }
+            gather(c2, r2 >= 0, g_nx);
+            chg_st = r2 >= 0 && r2 != cur;
+            if (chg_st) {
+                const char* src = own_base + (uint64_t)(unsigned)r2 * row_bytes;
+#pragma unroll
+                for (int v = 0; v < VPL; ++v)
+                    if (act[v]) own_nx[v] = ldg_pack(reinterpret_cast<const real*>(src + offb[v]));
+            }
+            r_st = r2;
+            y_st = y2;
+            // ---- reduce and accumulate the current step (pad / invalid lanes carry zeros)
+            real s0 = real(0), s1 = real(0);
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                s0 = fma(own[v].v[0], g[v].v[0], s0);
+                s1 = fma(own[v].v[1], g[v].v[1], s1);
+                if (EPV == 4) {
+                    s0 = fma(own[v].v[EPV - 2], g[v].v[EPV - 2], s0);
+                    s1 = fma(own[v].v[EPV - 1], g[v].v[EPV - 1], s1);
+                }
+            }
+            real s = s0 + s1;
+#pragma unroll
+            for (int o = LPG / 2; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o, LPG);
+            const real w = valid ? rdiv_fast(yy, s) : real(0);
+#pragma unroll
+            for (int v = 0; v < VPL; ++v)
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) sum[v].v[e] = fma(w, g[v].v[e], sum[v].v[e]);
+        }
+        r = rn;
+        c = cn;
+        y = yn;
+    }
+    if (cur >= 0) {
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+            if (act[v]) red_add_pack(acc + (size_t)cur * ld + (gl + LPG * v) * EPV, sum[v]);
+    }
+}
+
+// =============================================================================================
 // K2'  single-pass COO sweep with atomics on both sides: any nnz order, used for minibatches
 //      (partial_fit pxi:438-459, SVI pxi:292-314) and as the cross-check of the two-pass sweep.
 //      accU[u,:] += w_n * xi[i,:]    accI[i,:] += w_n * xu[u,:]     (optionally phi[n,:] written)

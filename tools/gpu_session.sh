@@ -2,8 +2,10 @@
 # One GPU-box session: tune -> bench / tests / profiles under the fastest verified configuration ->
 # the same under the shipped defaults.  Every step has its own timeout and writes under gpurun_out/,
 # most valuable first, so a clamped call still brings results back.
-#     gpurun --timeout 840 -- 'bash tools/gpu_session.sh'
+#     gpurun --timeout 840 -- 'bash tools/gpu_session.sh [tuner.py] [best.json key]'
 set -u
+TUNER=${1:-tune_r2.py}
+KEY=${2:-H_k50_alpha0.6}
 cd "$(dirname "$0")/.."
 OUT=gpurun_out
 mkdir -p $OUT
@@ -15,10 +17,10 @@ import os
 print("cpus", len(os.sched_getaffinity(0)))
 PY
 
-log "1 tune_r2"
-timeout 420 python tools/tune_r2.py --budget-s 120 > $OUT/tune_r2.log 2>&1
+log "1 $TUNER"
+timeout 420 python tools/$TUNER > $OUT/${TUNER%.py}.log 2>&1
 log "  rc=$?"
-eval "$(python tools/best_env.py H_k50_alpha0.6)"
+eval "$(python tools/best_env.py $KEY)"
 log "  winner: HPF_ROW_ALIGN=${HPF_ROW_ALIGN:-} HPF_OPTIONS=${HPF_OPTIONS:-}"
 
 log "2 bench under the winner"
@@ -29,10 +31,12 @@ log "3 parity + API tests under the winner"
 timeout 400 python -m pytest tests/test_gpu_parity.py tests/test_gpu_api.py -m gpu -x -q > $OUT/pytest_winner.log 2>&1
 log "  rc=$? $(tail -1 $OUT/pytest_winner.log)"
 
+if [ ! -s profiles/r01b_gather_probe_items.jsonl ]; then
 log "4 gather / RED ceiling probe"
 timeout 120 tools/bin/gather_probe --rows 380000 > $OUT/gather_probe_items.jsonl 2> $OUT/gather_probe.err
 timeout 90 tools/bin/gather_probe --rows 1000000 --quick > $OUT/gather_probe_users.jsonl 2>> $OUT/gather_probe.err
 log "  rc=$? $(wc -l < $OUT/gather_probe_items.jsonl) + $(wc -l < $OUT/gather_probe_users.jsonl) lines"
+fi
 
 log "5 ncu launch list under the winner"
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file $OUT/launches_winner.csv \
