@@ -138,6 +138,17 @@ __device__ __forceinline__ Pack<real> lds_pack(uint32_t addr) {
     return r;
 }
 
+// per-thread asynchronous 16-byte copy global -> shared (LDGSTS, L2-only caching) and its group fences:
+// the landing zone of the deep gather pipeline in sweep_major_v3_kernel
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // vector reduction into global memory: RED.E.ADD.F32x4 (sm_90+) for float, 2x RED.E.ADD.F64 for double
 __device__ __forceinline__ void red_add_pack(float* p, const Pack<float>& r) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]),

@@ -74,7 +74,14 @@ inline Shape default_shape_v2(int packs, int real_bytes) {
     if (real_bytes == 4 && packs == 32) return Shape{16, 3, 0};
     return Shape{0, 0, 0};
 }
-constexpr int kDefaultKernel = 1;  // 1 = sweep_major_kernel, 2 = sweep_major_v2_kernel (two-pass mode only)
+// shapes of the deep-pipeline two-pass kernel (option "kernel"=3)
+inline Shape default_shape_v3(int packs, int real_bytes) {
+    if (real_bytes == 4 && packs == 8) return Shape{8, 6, 0};
+    if (real_bytes == 4 && packs == 16) return Shape{8, 3, 0};
+    if (real_bytes == 4 && packs == 32) return Shape{16, 3, 0};
+    return Shape{0, 0, 0};
+}
+constexpr int kDefaultKernel = 1;  // two-pass mode: 1 sweep_major_kernel, 2 sweep_major_v2_kernel, 3 sweep_major_v3_kernel
 
 template <typename real_, int LPG, int VPL>
 struct Cfg {
@@ -461,6 +468,25 @@ int launch_sweep_v2(hpf_engine* h, const int* row, const int* col, const void* v
     return HPF_OK;
 }
 
+template <typename real, int LPG, int VPL, int MINB, int HINT>
+int launch_sweep_v3(hpf_engine* h, const int* row, const int* col, const void* val, const void* xown,
+                    const void* xgat, void* acc) {
+    auto kern = hpf::sweep_major_v3_kernel<real, LPG, VPL, MINB, HINT>;
+    constexpr int smem = 8 * 2 * 4 * VPL * 512;  // 8 warps x (gather ring + own ring) x 4 slots x VPL x 512 B
+    static thread_local bool configured = false;  // per instantiation (function-local static of a template)
+    if (!configured) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    const long long groups = (h->nnz + h->chunk - 1) / h->chunk;
+    const long long threads = groups * LPG;
+    kern<<<nblk(threads), 256, smem, h->stream>>>(row, col, (const real*)val, h->nnz, h->chunk, (const real*)xown,
+                                                  (const real*)xgat, (real*)acc, h->ld, h->kw);
+    h->launches++;
+    CKK();
+    return HPF_OK;
+}
+
 // staged-gather sweep (hpf_sweep_tma.cuh): 8 lanes per row, rows staged in shared memory by bulk copies
 template <typename real, int VPL, int MINB>
 int launch_sweep_tma_variant(hpf_engine* h, const int* row, const int* col, const void* val, const void* xown,
@@ -514,6 +540,29 @@ int launch_sweep_major(hpf_engine* h, const int* row, const int* col, const void
     const Shape def = default_shape(packs, (int)sizeof(real), fused);
     const int lpg = h->v_lpg ? h->v_lpg : def.lpg, mb = h->v_minb ? h->v_minb : def.minb;
     const int hint = h->v_hint >= 0 ? h->v_hint : def.hint;
+    if (!fused && h->kernel_ver == 3) {  // deep-pipeline two-pass kernel (sweep_major_v3_kernel, cp.async rings)
+        const Shape d3 = default_shape_v3(packs, (int)sizeof(real));
+        const int l3 = h->v_lpg ? h->v_lpg : d3.lpg, m3 = h->v_minb ? h->v_minb : d3.minb;
+        const int h3 = h->v_hint >= 0 ? h->v_hint : d3.hint;
+#define HPF_Q(L, M, H)                          \
+    if (l3 == L && m3 == M && h3 == H)          \
+        return launch_sweep_v3<real, L, packs / L, M, H>(h, row, col, val, xown, xgat, acc);
+        if constexpr (packs == 16 && sizeof(real) == 4) {
+            HPF_Q(8, 2, 0) HPF_Q(8, 3, 0) HPF_Q(8, 3, 1) HPF_Q(16, 3, 0) HPF_Q(16, 4, 0) HPF_Q(16, 5, 0) HPF_Q(16, 6, 0) HPF_Q(16, 4, 1)
+        }
+        if constexpr (packs == 8 && sizeof(real) == 4) {
+            HPF_Q(8, 4, 0) HPF_Q(8, 6, 0) HPF_Q(4, 2, 0) HPF_Q(4, 3, 0)
+        }
+        if constexpr (packs == 32 && sizeof(real) == 4) {
+            HPF_Q(16, 2, 0) HPF_Q(16, 3, 0) HPF_Q(32, 3, 0) HPF_Q(32, 4, 0) HPF_Q(32, 6, 0)
+        }
+#undef HPF_Q
+        if (h->strict && (h->v_lpg || h->v_minb || h->v_hint >= 0))
+            return fail(HPF_EINVAL, "no such deep-pipeline sweep shape for this row class (lpg=%d minb=%d hint=%d)", l3, m3, h3);
+        // generic shape (fp64, rows beyond 512 bytes): resident CTAs follow the shared-memory footprint
+        constexpr int gm = C::vpl == 1 ? 4 : (C::vpl == 2 ? 3 : 1);
+        return launch_sweep_v3<real, C::lpg, C::vpl, gm, 0>(h, row, col, val, xown, xgat, acc);
+    }
     if (!fused && h->kernel_ver == 2) {  // pipelined two-pass kernel (sweep_major_v2_kernel)
         const Shape d2 = default_shape_v2(packs, (int)sizeof(real));
         const int l2 = h->v_lpg ? h->v_lpg : d2.lpg, m2 = h->v_minb ? h->v_minb : d2.minb;
@@ -977,7 +1026,8 @@ int hpf_set_option(hpf_engine* h, const char* name, double value) {
     } else if (!strcmp(name, "unroll")) {
         if (value != 0 && value != 1) return fail(HPF_EINVAL, "unrolled sweep shapes were measured slower and removed (unroll must be 1)");
     } else if (!strcmp(name, "kernel")) {
-        if (value != 1 && value != 2) return fail(HPF_EINVAL, "kernel must be 1 (classic) or 2 (pipelined)");
+        if (value != 1 && value != 2 && value != 3)
+            return fail(HPF_EINVAL, "kernel must be 1 (classic), 2 (register pipeline) or 3 (cp.async pipeline)");
         h->kernel_ver = (int)value;
         drop_graphs(h);
     } else if (!strcmp(name, "strict")) {

@@ -351,6 +351,186 @@ sweep_major_v2_kernel(const int* __restrict__ row, const int* __restrict__ col, 
 }
 
 // =============================================================================================
+// K2 (deep-pipeline form) -- same contract again:
+//       acc[r, :] += sum_{n in segment} (Y[n] / dot(xown[r], xgat[c_n])) * xgat[c_n, :]
+// Measured (profiles/r01b_tune_v2.jsonl): the one-step register pipeline above still needs 1.45 ms per
+// pass where the bare gathers take 0.6 ms.  A warp advances one step per memory round trip, the round
+// trip is the MAXIMUM over its lane groups' loads (gathers that miss L2, own rows and triples streamed
+// from DRAM), and registers cap how many rows a warp can keep in flight.  Here the rows land in SHARED
+// memory instead: every lane copies its own 16-byte packs with cp.async (LDGSTS, per-thread, no
+// per-copy descriptor like the bulk/TMA path of hpf_sweep_tma.cuh) DEPTH-1 steps ahead of their use and
+// reads back exactly the packs it copied, so no barrier or cross-lane hand-off is needed.  The own row
+// of an upcoming major-id change is staged the same way in a second ring; triples are fetched two
+// batches ahead.  Control flow is warp-uniform (full-mask shuffles).
+//   shared memory per warp: 2 rings x DEPTH slots x VPL x 512 B.
+// =============================================================================================
+template <typename real, int LPG, int VPL, int MINB, int HINT>
+__global__ void __launch_bounds__(256, MINB)
+sweep_major_v3_kernel(const int* __restrict__ row, const int* __restrict__ col, const real* __restrict__ val,
+                      long long nnz, int chunk, const real* __restrict__ xown, const real* __restrict__ xgat,
+                      real* __restrict__ acc, int ld, int kw) {
+    constexpr int EPV = Pack<real>::N;
+    constexpr int DEPTH = 4;  // ring slots; LPG is a multiple of 4, so the slot of step t is t % 4 at compile time
+    static_assert(LPG % DEPTH == 0, "lane-group width must be a multiple of the ring depth");
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr uint32_t SLOT_BYTES = VPL * 32 * 16;            // one step of one warp: [v][lane] packs
+    constexpr uint32_t WARP_BYTES = 2 * DEPTH * SLOT_BYTES;   // gather ring, then own-row ring
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gl = lane % LPG;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (((tid - lane) / LPG) * (long long)chunk >= nnz) return;  // warp-uniform
+    const long long group = tid / LPG;
+    long long beg = group * (long long)chunk;
+    if (beg > nnz) beg = nnz;
+    const long long end = (beg + chunk < nnz) ? beg + chunk : nnz;
+    const int nbatch = (chunk + LPG - 1) / LPG;
+
+    uint64_t pol_stream = 0;
+    if (HINT) pol_stream = l2_policy_stream();
+    const unsigned row_bytes = (unsigned)ld * (unsigned)sizeof(real);
+    const char* gat_base = reinterpret_cast<const char*>(xgat);
+    const char* own_base = reinterpret_cast<const char*>(xown);
+    const uint32_t ring_g = smem_u32(smem_raw) + (uint32_t)warp * WARP_BYTES + (uint32_t)lane * 16u;
+    const uint32_t ring_o = ring_g + DEPTH * SLOT_BYTES;
+    unsigned offb[VPL];
+    bool act[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        offb[v] = (unsigned)((gl + LPG * v) * EPV) * (unsigned)sizeof(real);
+        act[v] = (gl + LPG * v) * EPV < kw;
+    }
+
+    auto load_triple = [&](long long idx, int& r, int& c, real& y) {
+        r = -1;
+        c = 0;
+        y = real(0);
+        if (idx < end) {
+            if (HINT) {
+                r = ldg_stream(row + idx, pol_stream);
+                c = ldg_stream(col + idx, pol_stream);
+                y = ldg_stream(val + idx, pol_stream);
+            } else {
+                r = __ldg(row + idx);
+                c = __ldg(col + idx);
+                y = __ldg(val + idx);
+            }
+        }
+    };
+    // stage one step: the gathered row always, the own row when the major id changes at that step
+    auto stage = [&](int slot, int ra, int ca, int r_before) {
+        if (ra >= 0) {
+            const char* src = gat_base + (uint64_t)(unsigned)ca * row_bytes;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v)
+                if (act[v]) cp_async16(ring_g + (uint32_t)slot * SLOT_BYTES + (uint32_t)v * 512u, src + offb[v]);
+            if (ra != r_before) {
+                const char* so = own_base + (uint64_t)(unsigned)ra * row_bytes;
+#pragma unroll
+                for (int v = 0; v < VPL; ++v)
+                    if (act[v]) cp_async16(ring_o + (uint32_t)slot * SLOT_BYTES + (uint32_t)v * 512u, so + offb[v]);
+            }
+        }
+        cp_async_commit();
+    };
+
+    Pack<real> own[VPL], sum[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        own[v] = pack_zero<real>();
+        sum[v] = pack_zero<real>();
+    }
+    int cur = -1;
+
+    // triples: batch b in (r0,c0,y0), b+1 in (r1,c1,y1), b+2 loaded at the top of batch b
+    int r0, c0, r1, c1, r2 = -1, c2 = 0;
+    real y0, y1, y2 = real(0);
+    load_triple(beg + gl, r0, c0, y0);
+    load_triple((1 < nbatch) ? beg + LPG + gl : end, r1, c1, y1);
+    // prologue: stage steps 0 .. DEPTH-2 (all inside batch 0 or, for LPG == 4... still batch 0: DEPTH-2 < LPG)
+    int r_staged = -1;  // major id of the most recently staged step
+#pragma unroll
+    for (int t = 0; t < DEPTH - 1; ++t) {
+        const int ra = __shfl_sync(FULL, r0, t, LPG);
+        const int ca = __shfl_sync(FULL, c0, t, LPG);
+        stage(t, ra, ca, r_staged);
+        if (ra >= 0) r_staged = ra;
+    }
+
+    for (int b = 0; b < nbatch; ++b) {
+        load_triple((b + 2 < nbatch) ? beg + (long long)(b + 2) * LPG + gl : end, r2, c2, y2);
+#pragma unroll
+        for (int t = 0; t < LPG; ++t) {
+            // ---- stage step t + DEPTH - 1 (this batch or the next one)
+            {
+                constexpr int LOOK = DEPTH - 1;
+                int ra, ca;
+                if (t + LOOK < LPG) {
+                    ra = __shfl_sync(FULL, r0, t + LOOK, LPG);
+                    ca = __shfl_sync(FULL, c0, t + LOOK, LPG);
+                } else {
+                    ra = __shfl_sync(FULL, r1, t + LOOK - LPG, LPG);
+                    ca = __shfl_sync(FULL, c1, t + LOOK - LPG, LPG);
+                }
+                stage((t + LOOK) % DEPTH, ra, ca, r_staged);
+                if (ra >= 0) r_staged = ra;
+            }
+            cp_async_wait<DEPTH - 1>();  // everything but the newest DEPTH-1 groups has landed: step t is in
+            // ---- consume step t
+            const int rr = __shfl_sync(FULL, r0, t, LPG);
+            const real yy = __shfl_sync(FULL, y0, t, LPG);
+            const bool valid = rr >= 0;
+            const int slot = t % DEPTH;
+            if (valid && rr != cur) {  // divergent between groups, no shuffles inside
+                if (cur >= 0) {
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v)
+                        if (act[v]) red_add_pack(acc + (size_t)cur * ld + (gl + LPG * v) * EPV, sum[v]);
+                }
+                cur = rr;
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) {
+                    own[v] = act[v] ? lds_pack<real>(ring_o + (uint32_t)slot * SLOT_BYTES + (uint32_t)v * 512u)
+                                    : pack_zero<real>();
+                    sum[v] = pack_zero<real>();
+                }
+            }
+            Pack<real> g[VPL];
+#pragma unroll
+            for (int v = 0; v < VPL; ++v)
+                g[v] = (valid && act[v]) ? lds_pack<real>(ring_g + (uint32_t)slot * SLOT_BYTES + (uint32_t)v * 512u)
+                                         : pack_zero<real>();
+            real s0 = real(0), s1 = real(0);
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                s0 = fma(own[v].v[0], g[v].v[0], s0);
+                s1 = fma(own[v].v[1], g[v].v[1], s1);
+                if (EPV == 4) {
+                    s0 = fma(own[v].v[EPV - 2], g[v].v[EPV - 2], s0);
+                    s1 = fma(own[v].v[EPV - 1], g[v].v[EPV - 1], s1);
+                }
+            }
+            real s = s0 + s1;
+#pragma unroll
+            for (int o = LPG / 2; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o, LPG);
+            const real w = valid ? rdiv_fast(yy, s) : real(0);
+#pragma unroll
+            for (int v = 0; v < VPL; ++v)
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) sum[v].v[e] = fma(w, g[v].v[e], sum[v].v[e]);
+        }
+        r0 = r1; c0 = c1; y0 = y1;
+        r1 = r2; c1 = c2; y1 = y2;
+    }
+    cp_async_wait<0>();
+    if (cur >= 0) {
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+            if (act[v]) red_add_pack(acc + (size_t)cur * ld + (gl + LPG * v) * EPV, sum[v]);
+    }
+}
+
+// =============================================================================================
 // K2'  single-pass COO sweep with atomics on both sides: any nnz order, used for minibatches
 //      (partial_fit pxi:438-459, SVI pxi:292-314) and as the cross-check of the two-pass sweep.
 //      accU[u,:] += w_n * xi[i,:]    accI[i,:] += w_n * xu[u,:]     (optionally phi[n,:] written)

@@ -117,6 +117,7 @@ def top(rows, n=10, f=lambda r: True):
 
 CLASSIC = dict(sweep=0, kernel=1, lpg=4, minb=3, hint=1, chunk=64)
 FUSED = dict(sweep=4, kernel=1, lpg=8, minb=3, hint=0, chunk=64)
+V3_CORE = [(8, 3, 0), (8, 2, 0), (8, 3, 1), (16, 3, 0), (16, 4, 0), (16, 5, 0), (16, 6, 0), (16, 4, 1)]
 V2_CORE = [(8, 3, 0), (8, 2, 0), (8, 4, 0), (8, 5, 0), (8, 6, 0), (8, 3, 1), (16, 3, 0), (16, 4, 0), (16, 5, 0),
            (16, 6, 0), (4, 2, 0), (4, 3, 0), (16, 4, 1)]
 
@@ -136,9 +137,13 @@ def main():
             continue
         results.append(st.run(ref, "classic", **CLASSIC))
         results.append(st.run(ref, "fused4", **FUSED))
-        for lpg, minb, hint in V2_CORE:
-            for chunk in (64, 256):
-                results.append(st.run(ref, "v2", sweep=0, kernel=2, lpg=lpg, minb=minb, hint=hint, chunk=chunk))
+        if "--skip-v2" not in sys.argv:
+            for lpg, minb, hint in V2_CORE:
+                for chunk in (64, 256):
+                    results.append(st.run(ref, "v2", sweep=0, kernel=2, lpg=lpg, minb=minb, hint=hint, chunk=chunk))
+        for lpg, minb, hint in V3_CORE:
+            for chunk in (64, 128, 256):
+                results.append(st.run(ref, "v3", sweep=0, kernel=3, lpg=lpg, minb=minb, hint=hint, chunk=chunk))
         if st is not s0:
             st.close()
     s0.close()
@@ -146,7 +151,7 @@ def main():
     for r in top(results, 15):
         print(json.dumps(r), flush=True)
     # chunk / panel refinement around the best pipelined shape
-    lead = top(results, 1, lambda r: r.get("kernel") == 2)
+    lead = top(results, 1, lambda r: r.get("kernel") in (2, 3))
     if lead:
         b = lead[0]
         for panel in sorted({b["panel_mb"], 40.0, 56.0}):
@@ -156,16 +161,17 @@ def main():
                 print("setup failed", panel, repr(exc)[:200], flush=True)
                 continue
             for chunk in (32, 64, 128, 512, 1024):
-                results.append(st.run(ref, "v2-refine", sweep=0, kernel=2, lpg=b["lpg"], minb=b["minb"], hint=b["hint"], chunk=chunk))
+                results.append(st.run(ref, "refine", sweep=0, kernel=b["kernel"], lpg=b["lpg"], minb=b["minb"], hint=b["hint"], chunk=chunk))
             st.close()
     h_top = top(results, 12)
     print("== H top 12 after refinement ==")
     for r in h_top:
         print(json.dumps(r), flush=True)
     best["H_k50_alpha0.6"] = as_env(h_top[0])
-    v2 = top(results, 1, lambda r: r.get("kernel") == 2)
-    if v2:
-        best["H_k50_alpha0.6_v2"] = as_env(v2[0])
+    for ver in (2, 3):
+        lead_v = top(results, 1, lambda r: r.get("kernel") == ver)
+        if lead_v:
+            best["H_k50_alpha0.6_v%d" % ver] = as_env(lead_v[0])
     best["H_k50_alpha0.6_classic"] = as_env(rec0)
     json.dump(best, open(os.path.join(ROOT, "gpurun_out", "best.json"), "w"), indent=1)
 
@@ -204,6 +210,8 @@ def main():
             resk.append(st.run(refk, "fused4-k%d" % k, sweep=4, kernel=1, chunk=64, **fused))
             for lpg, minb, hint in v2shapes:
                 resk.append(st.run(refk, "v2-k%d" % k, sweep=0, kernel=2, lpg=lpg, minb=minb, hint=hint, chunk=64))
+            for lpg, minb in ([(8, 4), (8, 6), (4, 2), (4, 3)] if k == 30 else [(16, 2), (16, 3), (32, 3), (32, 4), (32, 6)]):
+                resk.append(st.run(refk, "v3-k%d" % k, sweep=0, kernel=3, lpg=lpg, minb=minb, hint=0, chunk=64))
             st.close()
         print("== k=%d top 6 ==" % k)
         for r in top(resk, 6):
