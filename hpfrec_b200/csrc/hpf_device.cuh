@@ -149,6 +149,12 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+template <typename real>
+__device__ __forceinline__ void sts_pack(uint32_t addr, const Pack<real>& r) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&r);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+}
+
 // vector reduction into global memory: RED.E.ADD.F32x4 (sm_90+) for float, 2x RED.E.ADD.F64 for double
 __device__ __forceinline__ void red_add_pack(float* p, const Pack<float>& r) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]),
@@ -199,6 +205,16 @@ __device__ __forceinline__ double rexp(double x) { return exp(x); }
 // count / normaliser: 2-ulp MUFU division is ample for float (parity gate 1e-5), IEEE for double
 __device__ __forceinline__ float rdiv_fast(float a, float b) { return __fdividef(a, b); }
 __device__ __forceinline__ double rdiv_fast(double a, double b) { return a / b; }
+
+// count / normaliser with a bare MUFU.RCP (1 ulp) and one multiply: the deep-pipeline sweep is issue-bound,
+// and the normaliser is a sum of products of numbers in (0, 1] with at least one term equal to the
+// product of the two row maxima's neighbours -- far from the denormal range __fdividef guards against
+__device__ __forceinline__ float rdiv_rcp(float a, float b) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+    return a * r;
+}
+__device__ __forceinline__ double rdiv_rcp(double a, double b) { return a / b; }
 
 // digamma for x > 0.  The reference calls scipy.special.cython_special.psi (pxi:5, call sites
 // pxi:570/588/685/717), i.e. cephes `psi`: upward recurrence psi(x) = psi(x+1) - 1/x until x >= 10,

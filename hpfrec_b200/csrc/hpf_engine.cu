@@ -81,6 +81,11 @@ inline Shape default_shape_v3(int packs, int real_bytes) {
     if (real_bytes == 4 && packs == 32) return Shape{16, 3, 0};
     return Shape{0, 0, 0};
 }
+inline int default_block_v3(int packs, int real_bytes) {
+    (void)packs;
+    (void)real_bytes;
+    return 256;
+}
 constexpr int kDefaultKernel = 1;  // two-pass mode: 1 sweep_major_kernel, 2 sweep_major_v2_kernel, 3 sweep_major_v3_kernel
 
 template <typename real_, int LPG, int VPL>
@@ -247,6 +252,7 @@ struct hpf_engine {
     int sweep_mode = kDefaultSweepMode;
     int use_graph = 0;
     int v_lpg = 0, v_minb = 0, v_hint = -1;  // sweep-kernel shape overrides (0 / -1 = default of the row class)
+    int v_block = 0;                         // CTA size of the deep-pipeline kernel (0 = default)
     int strict = 0;                         // unknown shape = error instead of falling back to the default
     int kernel_ver = kDefaultKernel;        // two-pass sweep kernel: 1 classic, 2 pipelined
     int64_t launches = 0;
@@ -468,11 +474,11 @@ int launch_sweep_v2(hpf_engine* h, const int* row, const int* col, const void* v
     return HPF_OK;
 }
 
-template <typename real, int LPG, int VPL, int MINB, int HINT>
+template <typename real, int LPG, int VPL, int MINB, int HINT, int BLOCK>
 int launch_sweep_v3(hpf_engine* h, const int* row, const int* col, const void* val, const void* xown,
                     const void* xgat, void* acc) {
-    auto kern = hpf::sweep_major_v3_kernel<real, LPG, VPL, MINB, HINT>;
-    constexpr int smem = 8 * 2 * 4 * VPL * 512;  // 8 warps x (gather ring + own ring) x 4 slots x VPL x 512 B
+    auto kern = hpf::sweep_major_v3_kernel<real, LPG, VPL, MINB, HINT, BLOCK>;
+    constexpr int smem = (BLOCK / 32) * 2 * 4 * VPL * 512;  // warps x (gather ring + own ring) x 4 slots x VPL x 512 B
     static thread_local bool configured = false;  // per instantiation (function-local static of a template)
     if (!configured) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -480,8 +486,8 @@ int launch_sweep_v3(hpf_engine* h, const int* row, const int* col, const void* v
     }
     const long long groups = (h->nnz + h->chunk - 1) / h->chunk;
     const long long threads = groups * LPG;
-    kern<<<nblk(threads), 256, smem, h->stream>>>(row, col, (const real*)val, h->nnz, h->chunk, (const real*)xown,
-                                                  (const real*)xgat, (real*)acc, h->ld, h->kw);
+    kern<<<nblk(threads, BLOCK), BLOCK, smem, h->stream>>>(row, col, (const real*)val, h->nnz, h->chunk,
+                                                           (const real*)xown, (const real*)xgat, (real*)acc, h->ld, h->kw);
     h->launches++;
     CKK();
     return HPF_OK;
@@ -544,24 +550,27 @@ int launch_sweep_major(hpf_engine* h, const int* row, const int* col, const void
         const Shape d3 = default_shape_v3(packs, (int)sizeof(real));
         const int l3 = h->v_lpg ? h->v_lpg : d3.lpg, m3 = h->v_minb ? h->v_minb : d3.minb;
         const int h3 = h->v_hint >= 0 ? h->v_hint : d3.hint;
-#define HPF_Q(L, M, H)                          \
-    if (l3 == L && m3 == M && h3 == H)          \
-        return launch_sweep_v3<real, L, packs / L, M, H>(h, row, col, val, xown, xgat, acc);
+        const int b3 = h->v_block ? h->v_block : default_block_v3(packs, (int)sizeof(real));
+#define HPF_Q(L, M, H, B)                               \
+    if (l3 == L && m3 == M && h3 == H && b3 == B)       \
+        return launch_sweep_v3<real, L, packs / L, M, H, B>(h, row, col, val, xown, xgat, acc);
         if constexpr (packs == 16 && sizeof(real) == 4) {
-            HPF_Q(8, 2, 0) HPF_Q(8, 3, 0) HPF_Q(8, 3, 1) HPF_Q(16, 3, 0) HPF_Q(16, 4, 0) HPF_Q(16, 5, 0) HPF_Q(16, 6, 0) HPF_Q(16, 4, 1)
+            HPF_Q(4, 2, 0, 128) HPF_Q(4, 3, 0, 128) HPF_Q(4, 3, 1, 128)
+            HPF_Q(8, 2, 0, 256) HPF_Q(8, 3, 0, 256) HPF_Q(8, 4, 0, 128) HPF_Q(8, 6, 0, 128) HPF_Q(8, 2, 1, 256)
+            HPF_Q(16, 4, 0, 256) HPF_Q(16, 6, 0, 256)
         }
         if constexpr (packs == 8 && sizeof(real) == 4) {
-            HPF_Q(8, 4, 0) HPF_Q(8, 6, 0) HPF_Q(4, 2, 0) HPF_Q(4, 3, 0)
+            HPF_Q(4, 2, 0, 256) HPF_Q(4, 3, 0, 256) HPF_Q(4, 6, 0, 128) HPF_Q(8, 4, 0, 256) HPF_Q(8, 6, 0, 256)
         }
         if constexpr (packs == 32 && sizeof(real) == 4) {
-            HPF_Q(16, 2, 0) HPF_Q(16, 3, 0) HPF_Q(32, 3, 0) HPF_Q(32, 4, 0) HPF_Q(32, 6, 0)
+            HPF_Q(8, 2, 0, 128) HPF_Q(8, 3, 0, 128) HPF_Q(16, 2, 0, 256) HPF_Q(16, 3, 0, 256) HPF_Q(32, 4, 0, 256) HPF_Q(32, 6, 0, 256)
         }
 #undef HPF_Q
-        if (h->strict && (h->v_lpg || h->v_minb || h->v_hint >= 0))
-            return fail(HPF_EINVAL, "no such deep-pipeline sweep shape for this row class (lpg=%d minb=%d hint=%d)", l3, m3, h3);
+        if (h->strict && (h->v_lpg || h->v_minb || h->v_hint >= 0 || h->v_block))
+            return fail(HPF_EINVAL, "no such deep-pipeline sweep shape for this row class (lpg=%d minb=%d hint=%d block=%d)", l3, m3, h3, b3);
         // generic shape (fp64, rows beyond 512 bytes): resident CTAs follow the shared-memory footprint
         constexpr int gm = C::vpl == 1 ? 4 : (C::vpl == 2 ? 3 : 1);
-        return launch_sweep_v3<real, C::lpg, C::vpl, gm, 0>(h, row, col, val, xown, xgat, acc);
+        return launch_sweep_v3<real, C::lpg, C::vpl, gm, 0, 256>(h, row, col, val, xown, xgat, acc);
     }
     if (!fused && h->kernel_ver == 2) {  // pipelined two-pass kernel (sweep_major_v2_kernel)
         const Shape d2 = default_shape_v2(packs, (int)sizeof(real));
@@ -1022,6 +1031,10 @@ int hpf_set_option(hpf_engine* h, const char* name, double value) {
         if (!strcmp(name, "lpg")) h->v_lpg = value > 0 ? (int)value : 0;      // 0 = default of the row class
         if (!strcmp(name, "minb")) h->v_minb = value > 0 ? (int)value : 0;    // 0 = default
         if (!strcmp(name, "hint")) h->v_hint = (int)value;                    // -1 = default
+        drop_graphs(h);
+    } else if (!strcmp(name, "block")) {
+        if (value != 0 && value != 128 && value != 256) return fail(HPF_EINVAL, "block must be 0 (default), 128 or 256");
+        h->v_block = (int)value;
         drop_graphs(h);
     } else if (!strcmp(name, "unroll")) {
         if (value != 0 && value != 1) return fail(HPF_EINVAL, "unrolled sweep shapes were measured slower and removed (unroll must be 1)");

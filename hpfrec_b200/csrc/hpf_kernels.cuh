@@ -364,13 +364,14 @@ sweep_major_v2_kernel(const int* __restrict__ row, const int* __restrict__ col, 
 // batches ahead.  Control flow is warp-uniform (full-mask shuffles).
 //   shared memory per warp: 2 rings x DEPTH slots x VPL x 512 B.
 // =============================================================================================
-template <typename real, int LPG, int VPL, int MINB, int HINT>
-__global__ void __launch_bounds__(256, MINB)
+template <typename real, int LPG, int VPL, int MINB, int HINT, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, MINB)
 sweep_major_v3_kernel(const int* __restrict__ row, const int* __restrict__ col, const real* __restrict__ val,
                       long long nnz, int chunk, const real* __restrict__ xown, const real* __restrict__ xgat,
                       real* __restrict__ acc, int ld, int kw) {
     constexpr int EPV = Pack<real>::N;
     constexpr int DEPTH = 4;  // ring slots; LPG is a multiple of 4, so the slot of step t is t % 4 at compile time
+    constexpr int LOOK = DEPTH - 1;
     static_assert(LPG % DEPTH == 0, "lane-group width must be a multiple of the ring depth");
     constexpr unsigned FULL = 0xffffffffu;
     constexpr uint32_t SLOT_BYTES = VPL * 32 * 16;            // one step of one warp: [v][lane] packs
@@ -389,17 +390,18 @@ sweep_major_v3_kernel(const int* __restrict__ row, const int* __restrict__ col, 
     uint64_t pol_stream = 0;
     if (HINT) pol_stream = l2_policy_stream();
     const unsigned row_bytes = (unsigned)ld * (unsigned)sizeof(real);
-    const char* gat_base = reinterpret_cast<const char*>(xgat);
-    const char* own_base = reinterpret_cast<const char*>(xown);
     const uint32_t ring_g = smem_u32(smem_raw) + (uint32_t)warp * WARP_BYTES + (uint32_t)lane * 16u;
     const uint32_t ring_o = ring_g + DEPTH * SLOT_BYTES;
-    unsigned offb[VPL];
+    // every lane reads back exactly the cells it copies; cells of packs beyond the row's active width
+    // are never copied, so zeroing them once makes every later read a plain LDS (no per-step predication)
+#pragma unroll
+    for (int q = 0; q < 2 * DEPTH * VPL; ++q) sts_pack<real>(ring_g + (uint32_t)q * 512u, pack_zero<real>());
+    const unsigned off0 = (unsigned)(gl * EPV) * (unsigned)sizeof(real);  // byte offset of this lane's first pack
+    const char* gat_lane = reinterpret_cast<const char*>(xgat) + off0;
+    const char* own_lane = reinterpret_cast<const char*>(xown) + off0;
     bool act[VPL];
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-        offb[v] = (unsigned)((gl + LPG * v) * EPV) * (unsigned)sizeof(real);
-        act[v] = (gl + LPG * v) * EPV < kw;
-    }
+    for (int v = 0; v < VPL; ++v) act[v] = (gl + LPG * v) * EPV < kw;
 
     auto load_triple = [&](long long idx, int& r, int& c, real& y) {
         r = -1;
@@ -420,15 +422,17 @@ sweep_major_v3_kernel(const int* __restrict__ row, const int* __restrict__ col, 
     // stage one step: the gathered row always, the own row when the major id changes at that step
     auto stage = [&](int slot, int ra, int ca, int r_before) {
         if (ra >= 0) {
-            const char* src = gat_base + (uint64_t)(unsigned)ca * row_bytes;
+            const char* src = gat_lane + (uint64_t)(unsigned)ca * row_bytes;
 #pragma unroll
             for (int v = 0; v < VPL; ++v)
-                if (act[v]) cp_async16(ring_g + (uint32_t)slot * SLOT_BYTES + (uint32_t)v * 512u, src + offb[v]);
+                if (act[v])
+                    cp_async16(ring_g + (uint32_t)slot * SLOT_BYTES + (uint32_t)v * 512u, src + v * (LPG * 16));
             if (ra != r_before) {
-                const char* so = own_base + (uint64_t)(unsigned)ra * row_bytes;
+                const char* so = own_lane + (uint64_t)(unsigned)ra * row_bytes;
 #pragma unroll
                 for (int v = 0; v < VPL; ++v)
-                    if (act[v]) cp_async16(ring_o + (uint32_t)slot * SLOT_BYTES + (uint32_t)v * 512u, so + offb[v]);
+                    if (act[v])
+                        cp_async16(ring_o + (uint32_t)slot * SLOT_BYTES + (uint32_t)v * 512u, so + v * (LPG * 16));
             }
         }
         cp_async_commit();
@@ -447,40 +451,43 @@ sweep_major_v3_kernel(const int* __restrict__ row, const int* __restrict__ col, 
     real y0, y1, y2 = real(0);
     load_triple(beg + gl, r0, c0, y0);
     load_triple((1 < nbatch) ? beg + LPG + gl : end, r1, c1, y1);
-    // prologue: stage steps 0 .. DEPTH-2 (all inside batch 0 or, for LPG == 4... still batch 0: DEPTH-2 < LPG)
-    int r_staged = -1;  // major id of the most recently staged step
+    // prologue: stage steps 0 .. DEPTH-2 (inside batch 0 since DEPTH-2 < LPG); rq[] = major ids of the
+    // staged-but-not-consumed steps, oldest first
+    int r_staged = -1;  // major id of the most recently staged valid step
+    int rq[LOOK];
 #pragma unroll
-    for (int t = 0; t < DEPTH - 1; ++t) {
+    for (int t = 0; t < LOOK; ++t) {
         const int ra = __shfl_sync(FULL, r0, t, LPG);
         const int ca = __shfl_sync(FULL, c0, t, LPG);
         stage(t, ra, ca, r_staged);
         if (ra >= 0) r_staged = ra;
+        rq[t] = ra;
     }
 
     for (int b = 0; b < nbatch; ++b) {
         load_triple((b + 2 < nbatch) ? beg + (long long)(b + 2) * LPG + gl : end, r2, c2, y2);
 #pragma unroll
         for (int t = 0; t < LPG; ++t) {
-            // ---- stage step t + DEPTH - 1 (this batch or the next one)
-            {
-                constexpr int LOOK = DEPTH - 1;
-                int ra, ca;
-                if (t + LOOK < LPG) {
-                    ra = __shfl_sync(FULL, r0, t + LOOK, LPG);
-                    ca = __shfl_sync(FULL, c0, t + LOOK, LPG);
-                } else {
-                    ra = __shfl_sync(FULL, r1, t + LOOK - LPG, LPG);
-                    ca = __shfl_sync(FULL, c1, t + LOOK - LPG, LPG);
-                }
-                stage((t + LOOK) % DEPTH, ra, ca, r_staged);
-                if (ra >= 0) r_staged = ra;
+            // ---- stage step t + LOOK (this batch or the next one)
+            int ra, ca;
+            if (t + LOOK < LPG) {
+                ra = __shfl_sync(FULL, r0, t + LOOK, LPG);
+                ca = __shfl_sync(FULL, c0, t + LOOK, LPG);
+            } else {
+                ra = __shfl_sync(FULL, r1, t + LOOK - LPG, LPG);
+                ca = __shfl_sync(FULL, c1, t + LOOK - LPG, LPG);
             }
-            cp_async_wait<DEPTH - 1>();  // everything but the newest DEPTH-1 groups has landed: step t is in
+            stage((t + LOOK) % DEPTH, ra, ca, r_staged);
+            if (ra >= 0) r_staged = ra;
+            cp_async_wait<LOOK>();  // everything but the newest LOOK groups has landed: step t is in
             // ---- consume step t
-            const int rr = __shfl_sync(FULL, r0, t, LPG);
+            const int rr = rq[0];
+#pragma unroll
+            for (int q = 0; q + 1 < LOOK; ++q) rq[q] = rq[q + 1];
+            rq[LOOK - 1] = ra;
             const real yy = __shfl_sync(FULL, y0, t, LPG);
             const bool valid = rr >= 0;
-            const int slot = t % DEPTH;
+            const uint32_t slot_off = (uint32_t)(t % DEPTH) * SLOT_BYTES;
             if (valid && rr != cur) {  // divergent between groups, no shuffles inside
                 if (cur >= 0) {
 #pragma unroll
@@ -490,16 +497,13 @@ sweep_major_v3_kernel(const int* __restrict__ row, const int* __restrict__ col, 
                 cur = rr;
 #pragma unroll
                 for (int v = 0; v < VPL; ++v) {
-                    own[v] = act[v] ? lds_pack<real>(ring_o + (uint32_t)slot * SLOT_BYTES + (uint32_t)v * 512u)
-                                    : pack_zero<real>();
+                    own[v] = lds_pack<real>(ring_o + slot_off + (uint32_t)v * 512u);
                     sum[v] = pack_zero<real>();
                 }
             }
             Pack<real> g[VPL];
 #pragma unroll
-            for (int v = 0; v < VPL; ++v)
-                g[v] = (valid && act[v]) ? lds_pack<real>(ring_g + (uint32_t)slot * SLOT_BYTES + (uint32_t)v * 512u)
-                                         : pack_zero<real>();
+            for (int v = 0; v < VPL; ++v) g[v] = lds_pack<real>(ring_g + slot_off + (uint32_t)v * 512u);
             real s0 = real(0), s1 = real(0);
 #pragma unroll
             for (int v = 0; v < VPL; ++v) {
@@ -513,7 +517,8 @@ sweep_major_v3_kernel(const int* __restrict__ row, const int* __restrict__ col, 
             real s = s0 + s1;
 #pragma unroll
             for (int o = LPG / 2; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o, LPG);
-            const real w = valid ? rdiv_fast(yy, s) : real(0);
+            // steps past the end of the chunk read a stale (finite) slot: their weight is forced to zero
+            const real w = valid ? rdiv_rcp(yy, s) : real(0);
 #pragma unroll
             for (int v = 0; v < VPL; ++v)
 #pragma unroll

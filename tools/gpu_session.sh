@@ -18,7 +18,8 @@ print("cpus", len(os.sched_getaffinity(0)))
 PY
 
 log "1 $TUNER"
-timeout 420 python tools/$TUNER > $OUT/${TUNER%.py}.log 2>&1
+TUNER_NAME=${TUNER%% *}
+timeout 420 python tools/$TUNER > $OUT/${TUNER_NAME%.py}.log 2>&1
 log "  rc=$?"
 eval "$(python tools/best_env.py $KEY)"
 log "  winner: HPF_ROW_ALIGN=${HPF_ROW_ALIGN:-} HPF_OPTIONS=${HPF_OPTIONS:-}"
@@ -49,6 +50,7 @@ timeout 240 ncu --set full --clock-control none --import-source on -k regex:'swe
 log "  rc=$?"
 
 unset HPF_ROW_ALIGN HPF_OPTIONS
+if [ -n "${SKIP_SHIPPED:-}" ]; then log "done (shipped-defaults steps skipped)"; exit 0; fi
 log "7 bench, shipped defaults"
 timeout 240 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > $OUT/bench_shipped.json 2> $OUT/bench_shipped.err
 log "  rc=$? $(cut -c1-160 $OUT/bench_shipped.json)"

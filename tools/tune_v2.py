@@ -105,7 +105,7 @@ class Setup:
 
 
 def as_env(r):
-    keys = ("sweep", "kernel", "lpg", "minb", "hint", "chunk")
+    keys = ("sweep", "kernel", "lpg", "minb", "hint", "block", "chunk")
     opts = ["panel_mb=%g" % r["panel_mb"]] + ["%s=%d" % (kk, r[kk]) for kk in keys if kk in r]
     return {"HPF_ROW_ALIGN": str(r["row_align"]), "HPF_OPTIONS": ",".join(opts), "ms_iter": r.get("ms_iter"), "record": r}
 
@@ -117,7 +117,9 @@ def top(rows, n=10, f=lambda r: True):
 
 CLASSIC = dict(sweep=0, kernel=1, lpg=4, minb=3, hint=1, chunk=64)
 FUSED = dict(sweep=4, kernel=1, lpg=8, minb=3, hint=0, chunk=64)
-V3_CORE = [(8, 3, 0), (8, 2, 0), (8, 3, 1), (16, 3, 0), (16, 4, 0), (16, 5, 0), (16, 6, 0), (16, 4, 1)]
+# (lpg, minb, hint, block) of the deep-pipeline kernel
+V3_CORE = [(8, 2, 0, 256), (8, 3, 0, 256), (8, 4, 0, 128), (8, 6, 0, 128), (4, 2, 0, 128), (4, 3, 0, 128),
+           (16, 4, 0, 256), (16, 6, 0, 256)]
 V2_CORE = [(8, 3, 0), (8, 2, 0), (8, 4, 0), (8, 5, 0), (8, 6, 0), (8, 3, 1), (16, 3, 0), (16, 4, 0), (16, 5, 0),
            (16, 6, 0), (4, 2, 0), (4, 3, 0), (16, 4, 1)]
 
@@ -128,7 +130,9 @@ def main():
     rec0, ref = s0.run(None, "classic", **CLASSIC)
     results.append(rec0)
     print("classic:", json.dumps(rec0), flush=True)
-    plan = [(128, 48.0), (128, 32.0), (128, 24.0), (32, 48.0), (128, 64.0), (128, 96.0), (32, 32.0)]
+    plan = [(128, 96.0), (128, 64.0), (128, 48.0), (128, 128.0), (32, 96.0), (128, 32.0)]
+    if "--skip-v2" not in sys.argv:
+        plan += [(128, 24.0), (32, 48.0), (32, 32.0)]
     for align, panel in plan:
         try:
             st = s0 if (align, panel) == (32, 48.0) else Setup(50, 0.6, align, panel)
@@ -141,9 +145,9 @@ def main():
             for lpg, minb, hint in V2_CORE:
                 for chunk in (64, 256):
                     results.append(st.run(ref, "v2", sweep=0, kernel=2, lpg=lpg, minb=minb, hint=hint, chunk=chunk))
-        for lpg, minb, hint in V3_CORE:
-            for chunk in (64, 128, 256):
-                results.append(st.run(ref, "v3", sweep=0, kernel=3, lpg=lpg, minb=minb, hint=hint, chunk=chunk))
+        for lpg, minb, hint, block in V3_CORE:
+            for chunk in (128, 256, 512):
+                results.append(st.run(ref, "v3", sweep=0, kernel=3, lpg=lpg, minb=minb, hint=hint, block=block, chunk=chunk))
         if st is not s0:
             st.close()
     s0.close()
@@ -161,7 +165,8 @@ def main():
                 print("setup failed", panel, repr(exc)[:200], flush=True)
                 continue
             for chunk in (32, 64, 128, 512, 1024):
-                results.append(st.run(ref, "refine", sweep=0, kernel=b["kernel"], lpg=b["lpg"], minb=b["minb"], hint=b["hint"], chunk=chunk))
+                extra = {"block": b["block"]} if "block" in b else {}
+                results.append(st.run(ref, "refine", sweep=0, kernel=b["kernel"], lpg=b["lpg"], minb=b["minb"], hint=b["hint"], chunk=chunk, **extra))
             st.close()
     h_top = top(results, 12)
     print("== H top 12 after refinement ==")
@@ -187,7 +192,7 @@ def main():
     res9 = [rec9]
     for r in leaders[:3]:
         st = Setup(50, 0.9, r["row_align"], r["panel_mb"])
-        res9.append(st.run(ref9, "leader-alpha0.9", **{kk: r[kk] for kk in ("sweep", "kernel", "lpg", "minb", "hint", "chunk")}))
+        res9.append(st.run(ref9, "leader-alpha0.9", **{kk: r[kk] for kk in ("sweep", "kernel", "lpg", "minb", "hint", "block", "chunk") if kk in r}))
         st.close()
     print("== alpha 0.9 ==")
     for r in res9:
@@ -200,7 +205,7 @@ def main():
             (30, dict(lpg=4, minb=2, hint=0), dict(lpg=8, minb=6, hint=0), [(8, 4, 0), (8, 6, 0), (8, 8, 0), (4, 3, 0), (4, 4, 0), (4, 6, 0)]),
             (128, dict(lpg=8, minb=4, hint=0), dict(lpg=16, minb=4, hint=0), [(16, 3, 0), (16, 2, 0), (16, 4, 0), (32, 3, 0), (32, 4, 0), (8, 2, 0), (8, 3, 0)])):
         resk, refk = [], None
-        for align, panel in ((128, 48.0), (128, 24.0)):
+        for align, panel in ((128, 48.0), (128, 96.0)):
             st = Setup(k, 0.6, align, panel)
             if refk is None:
                 r, refk = st.run(None, "classic-k%d" % k, sweep=0, kernel=1, chunk=64, **classic)
@@ -208,10 +213,13 @@ def main():
             else:
                 resk.append(st.run(refk, "classic-k%d" % k, sweep=0, kernel=1, chunk=64, **classic))
             resk.append(st.run(refk, "fused4-k%d" % k, sweep=4, kernel=1, chunk=64, **fused))
-            for lpg, minb, hint in v2shapes:
-                resk.append(st.run(refk, "v2-k%d" % k, sweep=0, kernel=2, lpg=lpg, minb=minb, hint=hint, chunk=64))
-            for lpg, minb in ([(8, 4), (8, 6), (4, 2), (4, 3)] if k == 30 else [(16, 2), (16, 3), (32, 3), (32, 4), (32, 6)]):
-                resk.append(st.run(refk, "v3-k%d" % k, sweep=0, kernel=3, lpg=lpg, minb=minb, hint=0, chunk=64))
+            if "--skip-v2" not in sys.argv:
+                for lpg, minb, hint in v2shapes:
+                    resk.append(st.run(refk, "v2-k%d" % k, sweep=0, kernel=2, lpg=lpg, minb=minb, hint=hint, chunk=64))
+            for lpg, minb, block in ([(4, 2, 256), (4, 3, 256), (4, 6, 128), (8, 4, 256), (8, 6, 256)] if k == 30 else
+                                     [(8, 2, 128), (8, 3, 128), (16, 2, 256), (16, 3, 256), (32, 4, 256), (32, 6, 256)]):
+                for chunk in (64, 256):
+                    resk.append(st.run(refk, "v3-k%d" % k, sweep=0, kernel=3, lpg=lpg, minb=minb, hint=0, block=block, chunk=chunk))
             st.close()
         print("== k=%d top 6 ==" % k)
         for r in top(resk, 6):
