@@ -257,6 +257,7 @@ def run_ours(a):
     eng.load_state(Gs, Gr, Ls, Lr, kr, tr)
     eng.load_coo(lu, li, ly)
     ld = eng.ld
+    engine_config = eng.describe()
 
     if world > 1:
         partial = hdist.engine_partial_tensors(eng, local)
@@ -403,32 +404,50 @@ def run_ours(a):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src, "kernel": "whole iteration", "iteration": iteration}
     if phases is not None:
-        names = ["sweep_major_kernel(item-major pass)", "sweep_major_kernel(user-major pass)",
-                 "update_rows_kernel(users)", "update_rows_kernel(items)"]
         s = rb
-        # per-launch algorithmic bytes: triples once + own x read + gathered x read once + sums written
+        sweep_kernel = engine_config.get("kernel", "sweep kernel")
+        # per-launch algorithmic bytes of one pass: triples once + own x read + gathered x read once + sums written
         pass_bytes = [nnz * (4 + 4 + s) + (2 * nI + nUl) * k * s, nnz * (4 + 4 + s) + (2 * nUl + nI) * k * s]
+        # a one-pass (fused) sweep streams the triples once and touches all four factor / sum matrices once
+        fused_bytes = nnz * (4 + 4 + s) + 2 * (nUl + nI) * k * s
         upd_bytes = [4 * nUl * k * s, 4 * nI * k * s]  # x r/w, sums r/w(zero) (lean iteration)
         tot = sum(phases)
-        roofline["kernels"] = [
-            {"name": names[j], "ms": phases[j], "share": phases[j] / tot,
-             "algorithmic_bytes": int((pass_bytes + upd_bytes)[j]),
-             "achieved_gbs": (pass_bytes + upd_bytes)[j] / (phases[j] * 1e-3) / 1e9,
-             "frac": (pass_bytes + upd_bytes)[j] / (phases[j] * 1e-3) / 1e9 / peak} for j in range(4)]
-        # the contract's roofline object describes the DOMINANT kernel, per launch (2 launches / iteration)
-        dom_bytes = 0.5 * (pass_bytes[0] + pass_bytes[1])
-        dom_ms = 0.5 * (phases[0] + phases[1])
+        live = [j for j in (0, 1) if phases[j] > 0.02]  # a fused sweep leaves the other pass's slot empty
+        kernels = []
+        for j in live:
+            nbytes = pass_bytes[j] if len(live) == 2 else fused_bytes
+            label = ("item-major pass", "user-major pass")[j] if len(live) == 2 else "one fused %s pass" % ("item-major", "user-major")[j]
+            kernels.append({"name": "%s (%s)" % (sweep_kernel, label), "ms": phases[j], "share": phases[j] / tot,
+                            "algorithmic_bytes": int(nbytes), "achieved_gbs": nbytes / (phases[j] * 1e-3) / 1e9,
+                            "frac": nbytes / (phases[j] * 1e-3) / 1e9 / peak})
+        for j, nm in ((2, "update_rows_kernel (users)"), (3, "update_rows_kernel (items)")):
+            kernels.append({"name": nm, "ms": phases[j], "share": phases[j] / tot, "algorithmic_bytes": int(upd_bytes[j - 2]),
+                            "achieved_gbs": upd_bytes[j - 2] / (phases[j] * 1e-3) / 1e9,
+                            "frac": upd_bytes[j - 2] / (phases[j] * 1e-3) / 1e9 / peak})
+        roofline["kernels"] = kernels
+        # the contract's roofline object describes the DOMINANT kernel, per launch
+        dom = kernels[:len(live)]
+        dom_bytes = sum(kk["algorithmic_bytes"] for kk in dom) / len(dom)
+        dom_ms = sum(kk["ms"] for kk in dom) / len(dom)
         dom_achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
-        roofline.update({"kernel": "sweep_major_kernel (2 launches per iteration; per-launch averages)",
+        roofline.update({"kernel": "%s (%d launch%s per iteration; per-launch averages)" % (
+                             sweep_kernel, len(dom), "es" if len(dom) > 1 else ""),
                          "achieved": dom_achieved, "frac": dom_achieved / peak,
                          "algorithmic_bytes_per_launch": int(dom_bytes), "ms_per_launch": dom_ms,
-                         "share_of_step": (phases[0] + phases[1]) / tot})
-        try:  # measured DRAM bytes per launch of that kernel from the committed ncu capture (same workload only)
+                         "share_of_step": sum(kk["ms"] for kk in dom) / tot})
+        try:  # measured DRAM bytes per launch of that kernel from the committed ncu capture (same workload + kernel only)
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            if tr.get("workload") == "%dx%dx%d k=%d %s" % (nU, nI, nnz, k, a.dtype):
-                sw = tr["sweep_major_kernel"]
-                roofline["traffic"] = int(0.5 * sum(v["dram_read_bytes"] + v["dram_write_bytes"] for v in sw.values()))
+            if tr.get("workload") == "%dx%dx%d k=%d %s" % (nU, nI, nnz, k, a.dtype) and tr.get("kernel") == sweep_kernel:
+                sw = tr["sweep_launches"]
+                roofline["traffic"] = int(sum(v["dram_read_bytes"] + v["dram_write_bytes"] for v in sw) / len(sw))
                 roofline["traffic_source"] = "profiles/traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch)"
+        except Exception:
+            pass
+        try:  # the measured ceiling of the bare row-gather pattern (tools/gather_probe.cu), for context
+            gc = json.load(open(os.path.join(ROOT, "profiles", "gather_ceiling.json")))
+            if gc.get("workload") == "%dx%dx%d k=%d %s" % (nU, nI, nnz, k, a.dtype):
+                roofline["gather_ceiling"] = {"ms_per_pass": gc["ms_per_pass"], "frac_of_ceiling": gc["ms_per_pass"] / dom_ms,
+                                              "source": gc["source"]}
         except Exception:
             pass
 
@@ -443,7 +462,8 @@ def run_ours(a):
                        "materialize": "shape/rate matrices stored on the last iteration of each call; "
                                       "intermediate iterations keep the equivalent per-row factors" if world == 1
                                       else "every iteration"},
-            "nnz_per_s": value * nnz, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+            "nnz_per_s": value * nnz, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "engine": engine_config}
     if e2e is not None:
         line["e2e"] = e2e
     if not a.no_cpu_baseline:

@@ -50,6 +50,7 @@ SIGNATURES = {
     "hpf_launch_count": ([_P, _c.POINTER(_I64)], _c.c_int),
     "hpf_phase_ms": ([_P, _c.POINTER(_D), _c.POINTER(_I64)], _c.c_int),
     "hpf_ld": ([_P, _c.POINTER(_I32)], _c.c_int),
+    "hpf_describe": ([_P, _c.c_char_p, _I64], _c.c_int),
 }
 
 _lib = None

@@ -138,6 +138,21 @@ __device__ __forceinline__ Pack<real> lds_pack(uint32_t addr) {
     return r;
 }
 
+// four consecutive triples with 128-bit loads (read-only path); all lanes of a group read the same address
+__device__ __forceinline__ void ldg4(const int* p, int (&v)[4]) {
+    const int4 q = __ldg(reinterpret_cast<const int4*>(p));
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+}
+__device__ __forceinline__ void ldg4(const float* p, float (&v)[4]) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+}
+__device__ __forceinline__ void ldg4(const double* p, double (&v)[4]) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(p));
+    const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
 // per-thread asynchronous 16-byte copy global -> shared (LDGSTS, L2-only caching) and its group fences:
 // the landing zone of the deep gather pipeline in sweep_major_v3_kernel
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {

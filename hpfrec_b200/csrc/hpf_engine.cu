@@ -52,9 +52,9 @@ int fail(int code, const char* fmt, ...) {
 // in this block; each value is also an option (hpf_set_option / HPF_OPTIONS / HPF_ROW_ALIGN), so the
 // test-suite and the bench can be run under a candidate configuration before it becomes the default.
 // -------------------------------------------------------------------------------------------------
-constexpr int kDefaultRowAlign = 32;     // bytes; row stride rule in hpf_create
-constexpr double kDefaultPanelMb = 48.0;  // L2 panel of the gathered factor side
-constexpr int kDefaultChunk = 64;        // nnz walked by one lane group
+constexpr int kDefaultRowAlign = 128;    // bytes; row stride rule in hpf_create (cache-line aligned rows)
+constexpr double kDefaultPanelMb = 96.0;  // L2 panel of the gathered factor side
+constexpr int kDefaultChunk = 256;       // nnz walked by one lane group
 constexpr int kDefaultSweepMode = 0;     // 0 two-pass, 2 fused user-major, 4 fused item-major
 
 struct Shape {
@@ -75,18 +75,17 @@ inline Shape default_shape_v2(int packs, int real_bytes) {
     return Shape{0, 0, 0};
 }
 // shapes of the deep-pipeline two-pass kernel (option "kernel"=3)
+// (measured on the H data at k = 30 / 50 / 128: profiles/r01b_tune_v3b.jsonl)
 inline Shape default_shape_v3(int packs, int real_bytes) {
-    if (real_bytes == 4 && packs == 8) return Shape{8, 6, 0};
-    if (real_bytes == 4 && packs == 16) return Shape{8, 3, 0};
-    if (real_bytes == 4 && packs == 32) return Shape{16, 3, 0};
+    if (real_bytes == 4 && packs == 8) return Shape{4, 2, 0};
+    if (real_bytes == 4 && packs == 16) return Shape{8, 2, 0};
+    if (real_bytes == 4 && packs == 32) return Shape{8, 3, 0};
     return Shape{0, 0, 0};
 }
 inline int default_block_v3(int packs, int real_bytes) {
-    (void)packs;
-    (void)real_bytes;
-    return 256;
+    return (real_bytes == 4 && packs == 32) ? 128 : 256;  // 4 packs per lane: 16 KB of rings per warp
 }
-constexpr int kDefaultKernel = 1;  // two-pass mode: 1 sweep_major_kernel, 2 sweep_major_v2_kernel, 3 sweep_major_v3_kernel
+constexpr int kDefaultKernel = 3;  // two-pass mode: 1 sweep_major_kernel, 2 sweep_major_v2_kernel, 3 sweep_major_v3_kernel
 
 template <typename real_, int LPG, int VPL>
 struct Cfg {
@@ -398,9 +397,10 @@ int download_matrix(hpf_engine* h, const void* src, const void* denom, void* dst
 template <typename real>
 int build_order(hpf_engine* h, const int* major, const int* minor, const real* val, int64_t n,
                 int64_t n_major, int64_t n_minor, int** o_row, int** o_col, void** o_val) {
-    CK(hpf_malloc(o_row, sizeof(int) * (size_t)(n > 0 ? n : 1)));
-    CK(hpf_malloc(o_col, sizeof(int) * (size_t)(n > 0 ? n : 1)));
-    CK(hpf_malloc(o_val, sizeof(real) * (size_t)(n > 0 ? n : 1)));
+    // 8 spare entries: the vector-load sweep reads whole groups of four triples (masked past the end)
+    CK(hpf_malloc(o_row, sizeof(int) * (size_t)(n + 8)));
+    CK(hpf_malloc(o_col, sizeof(int) * (size_t)(n + 8)));
+    CK(hpf_malloc(o_val, sizeof(real) * (size_t)(n + 8)));
     if (n == 0) return HPF_OK;
     // panels: the gathered (minor) factor matrix is cut so one panel stays L2-resident
     const double minor_bytes = (double)n_minor * h->ld * h->rb;
@@ -493,6 +493,25 @@ int launch_sweep_v3(hpf_engine* h, const int* row, const int* col, const void* v
     return HPF_OK;
 }
 
+template <typename real, int LPG, int VPL, int MINB, int HINT, int BLOCK>
+int launch_sweep_v4(hpf_engine* h, const int* row, const int* col, const void* val, const void* xown,
+                    const void* xgat, void* acc) {
+    auto kern = hpf::sweep_major_v4_kernel<real, LPG, VPL, MINB, HINT, BLOCK>;
+    constexpr int smem = (BLOCK / 32) * 2 * 4 * VPL * 512;
+    static thread_local bool configured = false;
+    if (!configured) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    const long long groups = (h->nnz + h->chunk - 1) / h->chunk;
+    const long long threads = groups * LPG;
+    kern<<<nblk(threads, BLOCK), BLOCK, smem, h->stream>>>(row, col, (const real*)val, h->nnz, h->chunk,
+                                                           (const real*)xown, (const real*)xgat, (real*)acc, h->ld, h->kw);
+    h->launches++;
+    CKK();
+    return HPF_OK;
+}
+
 // staged-gather sweep (hpf_sweep_tma.cuh): 8 lanes per row, rows staged in shared memory by bulk copies
 template <typename real, int VPL, int MINB>
 int launch_sweep_tma_variant(hpf_engine* h, const int* row, const int* col, const void* val, const void* xown,
@@ -546,7 +565,29 @@ int launch_sweep_major(hpf_engine* h, const int* row, const int* col, const void
     const Shape def = default_shape(packs, (int)sizeof(real), fused);
     const int lpg = h->v_lpg ? h->v_lpg : def.lpg, mb = h->v_minb ? h->v_minb : def.minb;
     const int hint = h->v_hint >= 0 ? h->v_hint : def.hint;
-    if (!fused && h->kernel_ver == 3) {  // deep-pipeline two-pass kernel (sweep_major_v3_kernel, cp.async rings)
+    if (!fused && h->kernel_ver == 4 && h->chunk % 4 == 0) {  // deep pipeline with vector-loaded triples
+        const Shape d4 = default_shape_v3(packs, (int)sizeof(real));
+        const int l4 = h->v_lpg ? h->v_lpg : d4.lpg, m4 = h->v_minb ? h->v_minb : d4.minb;
+        const int b4 = h->v_block ? h->v_block : default_block_v3(packs, (int)sizeof(real));
+#define HPF_R(L, M, B)                          \
+    if (l4 == L && m4 == M && b4 == B)          \
+        return launch_sweep_v4<real, L, packs / L, M, 0, B>(h, row, col, val, xown, xgat, acc);
+        if constexpr (packs == 16 && sizeof(real) == 4) {
+            HPF_R(8, 2, 256) HPF_R(8, 3, 256) HPF_R(4, 2, 128) HPF_R(4, 3, 128) HPF_R(16, 4, 256) HPF_R(8, 4, 128)
+        }
+        if constexpr (packs == 8 && sizeof(real) == 4) {
+            HPF_R(4, 2, 256) HPF_R(4, 3, 256) HPF_R(8, 4, 256)
+        }
+        if constexpr (packs == 32 && sizeof(real) == 4) {
+            HPF_R(8, 3, 128) HPF_R(8, 2, 128) HPF_R(16, 2, 256) HPF_R(16, 3, 256)
+        }
+#undef HPF_R
+        if (h->strict && (h->v_lpg || h->v_minb || h->v_block))
+            return fail(HPF_EINVAL, "no such vector-triple sweep shape for this row class (lpg=%d minb=%d block=%d)", l4, m4, b4);
+        constexpr int gm4 = C::vpl == 1 ? 4 : (C::vpl == 2 ? 3 : 1);
+        return launch_sweep_v4<real, C::lpg, C::vpl, gm4, 0, 256>(h, row, col, val, xown, xgat, acc);
+    }
+    if (!fused && (h->kernel_ver == 3 || h->kernel_ver == 4)) {  // deep-pipeline two-pass kernel (sweep_major_v3_kernel, cp.async rings)
         const Shape d3 = default_shape_v3(packs, (int)sizeof(real));
         const int l3 = h->v_lpg ? h->v_lpg : d3.lpg, m3 = h->v_minb ? h->v_minb : d3.minb;
         const int h3 = h->v_hint >= 0 ? h->v_hint : d3.hint;
@@ -1039,8 +1080,8 @@ int hpf_set_option(hpf_engine* h, const char* name, double value) {
     } else if (!strcmp(name, "unroll")) {
         if (value != 0 && value != 1) return fail(HPF_EINVAL, "unrolled sweep shapes were measured slower and removed (unroll must be 1)");
     } else if (!strcmp(name, "kernel")) {
-        if (value != 1 && value != 2 && value != 3)
-            return fail(HPF_EINVAL, "kernel must be 1 (classic), 2 (register pipeline) or 3 (cp.async pipeline)");
+        if (value != 1 && value != 2 && value != 3 && value != 4)
+            return fail(HPF_EINVAL, "kernel must be 1 (classic), 2 (register pipeline), 3 (cp.async pipeline) or 4 (cp.async pipeline, vector-loaded triples)");
         h->kernel_ver = (int)value;
         drop_graphs(h);
     } else if (!strcmp(name, "strict")) {
@@ -1364,6 +1405,37 @@ int hpf_phase_ms(hpf_engine* h, double out[4], int64_t* iterations) {
     if (!h || !out) return fail(HPF_EINVAL, "NULL argument");
     for (int p = 0; p < 4; ++p) out[p] = h->phase_ms[p];
     if (iterations) *iterations = h->phase_iters;
+    return HPF_OK;
+}
+
+int hpf_describe(hpf_engine* h, char* buf, int64_t n) {
+    if (!h || !buf || n <= 0) return fail(HPF_EINVAL, "engine or buffer is NULL");
+    const int packs_row = h->ld * h->rb / 16;
+    int cls = 8;
+    while (cls < packs_row) cls *= 2;
+    const bool fused = h->sweep_mode == 2 || h->sweep_mode == 4;
+    Shape d = default_shape(cls, h->rb, fused);
+    const char* kern = fused ? "sweep_major_kernel<FUSE>" : "sweep_major_kernel";
+    int block = 256;
+    if (!fused && h->sweep_mode == 0 && h->kernel_ver == 2) {
+        d = default_shape_v2(cls, h->rb);
+        kern = "sweep_major_v2_kernel";
+    } else if (!fused && h->sweep_mode == 0 && (h->kernel_ver == 3 || h->kernel_ver == 4)) {
+        d = default_shape_v3(cls, h->rb);
+        kern = (h->kernel_ver == 4 && h->chunk % 4 == 0) ? "sweep_major_v4_kernel" : "sweep_major_v3_kernel";
+        block = h->v_block ? h->v_block : default_block_v3(cls, h->rb);
+    } else if (h->sweep_mode == 1) {
+        kern = "sweep_coo_kernel";
+    } else if (h->sweep_mode == 3) {
+        kern = "sweep_tma_kernel";
+    }
+    const int lpg = h->v_lpg ? h->v_lpg : d.lpg, minb = h->v_minb ? h->v_minb : d.minb;
+    const int hint = h->v_hint >= 0 ? h->v_hint : d.hint;
+    snprintf(buf, (size_t)n,
+             "real_bytes=%d k=%d kw=%d ld=%d sweep=%d kernel=%s lpg=%d minb=%d hint=%d block=%d chunk=%d panel_mb=%g "
+             "panels_user_major=%d panels_item_major=%d launches_per_iteration=%d",
+             h->rb, h->k, h->kw, h->ld, h->sweep_mode, kern, lpg, minb, hint, block, h->chunk, h->panel_mb, h->panelsA,
+             h->panelsB, (h->sweep_mode == 0 || h->sweep_mode == 3) ? 4 : 3);
     return HPF_OK;
 }
 

@@ -536,6 +536,172 @@ sweep_major_v3_kernel(const int* __restrict__ row, const int* __restrict__ col, 
 }
 
 // =============================================================================================
+// K2 (deep pipeline, shuffle-free triples).  ncu on the form above (profiles/r01b_ncu_full_v3_pipeline.csv):
+// memory latency is hidden (long-scoreboard stalls 0.2 per issue) and the kernel is bound by the LSU pipe
+// (59 %) / issue (66 %); of the ~10 LSU instructions per step, six are shuffles -- three of them only
+// broadcast the step's (major id, minor id, count) from the lane that loaded it.  Here every lane
+// reads the triples of FOUR consecutive steps itself with one 128-bit load per array (all lanes of a
+// group read the same address, one sector), so the only shuffles left are the butterfly of the
+// normaliser.  Batches are 4 steps (= the ring depth) for every lane-group width; needs chunk % 4 == 0
+// and triple arrays padded by 4 entries (the host falls back to the form above otherwise).
+// =============================================================================================
+template <typename real, int LPG, int VPL, int MINB, int HINT, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, MINB)
+sweep_major_v4_kernel(const int* __restrict__ row, const int* __restrict__ col, const real* __restrict__ val,
+                      long long nnz, int chunk, const real* __restrict__ xown, const real* __restrict__ xgat,
+                      real* __restrict__ acc, int ld, int kw) {
+    constexpr int EPV = Pack<real>::N;
+    constexpr int DEPTH = 4, LOOK = DEPTH - 1, B4 = 4;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr uint32_t SLOT_BYTES = VPL * 32 * 16;
+    constexpr uint32_t WARP_BYTES = 2 * DEPTH * SLOT_BYTES;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gl = lane % LPG;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (((tid - lane) / LPG) * (long long)chunk >= nnz) return;  // warp-uniform
+    const long long group = tid / LPG;
+    long long beg = group * (long long)chunk;
+    if (beg > nnz) beg = nnz;
+    const long long end = (beg + chunk < nnz) ? beg + chunk : nnz;
+    const int nbatch = (chunk + B4 - 1) / B4;
+
+    const unsigned row_bytes = (unsigned)ld * (unsigned)sizeof(real);
+    const uint32_t ring_g = smem_u32(smem_raw) + (uint32_t)warp * WARP_BYTES + (uint32_t)lane * 16u;
+    const uint32_t ring_o = ring_g + DEPTH * SLOT_BYTES;
+#pragma unroll
+    for (int q = 0; q < 2 * DEPTH * VPL; ++q) sts_pack<real>(ring_g + (uint32_t)q * 512u, pack_zero<real>());
+    const unsigned off0 = (unsigned)(gl * EPV) * (unsigned)sizeof(real);
+    const char* gat_lane = reinterpret_cast<const char*>(xgat) + off0;
+    const char* own_lane = reinterpret_cast<const char*>(xown) + off0;
+    bool act[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) act[v] = (gl + LPG * v) * EPV < kw;
+
+    // one batch = 4 consecutive triples, identical in every lane of the group; entries past the end of
+    // the chunk get major id -1
+    auto load_batch = [&](long long idx, int (&r)[4], int (&c)[4], real (&y)[4]) {
+        if (idx < end) {
+            ldg4(row + idx, r);
+            ldg4(col + idx, c);
+            ldg4(val + idx, y);
+#pragma unroll
+            for (int j = 1; j < 4; ++j)
+                if (idx + j >= end) r[j] = -1;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                r[j] = -1;
+                c[j] = 0;
+                y[j] = real(0);
+            }
+        }
+    };
+    auto stage = [&](int slot, int ra, int ca, int r_before) {
+        if (ra >= 0) {
+            const char* src = gat_lane + (uint64_t)(unsigned)ca * row_bytes;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v)
+                if (act[v])
+                    cp_async16(ring_g + (uint32_t)slot * SLOT_BYTES + (uint32_t)v * 512u, src + v * (LPG * 16));
+            if (ra != r_before) {
+                const char* so = own_lane + (uint64_t)(unsigned)ra * row_bytes;
+#pragma unroll
+                for (int v = 0; v < VPL; ++v)
+                    if (act[v])
+                        cp_async16(ring_o + (uint32_t)slot * SLOT_BYTES + (uint32_t)v * 512u, so + v * (LPG * 16));
+            }
+        }
+        cp_async_commit();
+    };
+
+    Pack<real> own[VPL], sum[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        own[v] = pack_zero<real>();
+        sum[v] = pack_zero<real>();
+    }
+    int cur = -1;
+
+    int rA[4], cA[4], rB[4], cB[4], rC[4], cC[4];
+    real yA[4], yB[4], yC[4];
+    load_batch(beg, rA, cA, yA);
+    load_batch(beg + B4, rB, cB, yB);
+    int r_staged = -1;
+    int rq[LOOK];
+#pragma unroll
+    for (int t = 0; t < LOOK; ++t) {
+        stage(t, rA[t], cA[t], r_staged);
+        if (rA[t] >= 0) r_staged = rA[t];
+        rq[t] = rA[t];
+    }
+
+    for (int b = 0; b < nbatch; ++b) {
+        load_batch(beg + (long long)(b + 2) * B4, rC, cC, yC);
+#pragma unroll
+        for (int t = 0; t < B4; ++t) {
+            const int ra = (t + LOOK < B4) ? rA[(t + LOOK) % B4] : rB[(t + LOOK) % B4];
+            const int ca = (t + LOOK < B4) ? cA[(t + LOOK) % B4] : cB[(t + LOOK) % B4];
+            stage((t + LOOK) % DEPTH, ra, ca, r_staged);
+            if (ra >= 0) r_staged = ra;
+            cp_async_wait<LOOK>();
+            const int rr = rq[0];
+#pragma unroll
+            for (int q = 0; q + 1 < LOOK; ++q) rq[q] = rq[q + 1];
+            rq[LOOK - 1] = ra;
+            const real yy = yA[t];
+            const bool valid = rr >= 0;
+            const uint32_t slot_off = (uint32_t)(t % DEPTH) * SLOT_BYTES;
+            if (valid && rr != cur) {
+                if (cur >= 0) {
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v)
+                        if (act[v]) red_add_pack(acc + (size_t)cur * ld + (gl + LPG * v) * EPV, sum[v]);
+                }
+                cur = rr;
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) {
+                    own[v] = lds_pack<real>(ring_o + slot_off + (uint32_t)v * 512u);
+                    sum[v] = pack_zero<real>();
+                }
+            }
+            Pack<real> g[VPL];
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) g[v] = lds_pack<real>(ring_g + slot_off + (uint32_t)v * 512u);
+            real s0 = real(0), s1 = real(0);
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                s0 = fma(own[v].v[0], g[v].v[0], s0);
+                s1 = fma(own[v].v[1], g[v].v[1], s1);
+                if (EPV == 4) {
+                    s0 = fma(own[v].v[EPV - 2], g[v].v[EPV - 2], s0);
+                    s1 = fma(own[v].v[EPV - 1], g[v].v[EPV - 1], s1);
+                }
+            }
+            real s = s0 + s1;
+#pragma unroll
+            for (int o = LPG / 2; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o, LPG);
+            const real w = valid ? rdiv_rcp(yy, s) : real(0);
+#pragma unroll
+            for (int v = 0; v < VPL; ++v)
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) sum[v].v[e] = fma(w, g[v].v[e], sum[v].v[e]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            rA[j] = rB[j]; cA[j] = cB[j]; yA[j] = yB[j];
+            rB[j] = rC[j]; cB[j] = cC[j]; yB[j] = yC[j];
+        }
+    }
+    cp_async_wait<0>();
+    if (cur >= 0) {
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+            if (act[v]) red_add_pack(acc + (size_t)cur * ld + (gl + LPG * v) * EPV, sum[v]);
+    }
+}
+
+// =============================================================================================
 // K2'  single-pass COO sweep with atomics on both sides: any nnz order, used for minibatches
 //      (partial_fit pxi:438-459, SVI pxi:292-314) and as the cross-check of the two-pass sweep.
 //      accU[u,:] += w_n * xi[i,:]    accI[i,:] += w_n * xu[u,:]     (optionally phi[n,:] written)

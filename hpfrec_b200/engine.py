@@ -101,6 +101,12 @@ class Engine:
         _lib.check(self._lib.hpf_ld(self._h, ctypes.byref(out)))
         return out.value
 
+    def describe(self):
+        """Resolved configuration as a dict of strings (row stride, sweep mode, kernel, shape, panels)."""
+        buf = ctypes.create_string_buffer(512)
+        _lib.check(self._lib.hpf_describe(self._h, buf, 512))
+        return dict(item.split("=", 1) for item in buf.value.decode().split())
+
     @property
     def launch_count(self):
         out = ctypes.c_int64()

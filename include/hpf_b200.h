@@ -54,9 +54,20 @@ int hpf_set_constants(hpf_engine* h, double a, double c, double k_shp, double t_
                       double add_k_rte, double add_t_rte);
 /* CUDA stream (cudaStream_t) all engine work is issued on; default: the legacy default stream. */
 int hpf_set_stream(hpf_engine* h, void* cuda_stream);
-/* Tunables: "panel_mb" (L2 panel size of the gathered factor side), "chunk" (nnz per lane group),
- * "use_graph" (0/1: replay one CAVI iteration as a CUDA graph), "sweep" (0 = two-pass segmented,
- * 1 = single-pass COO atomics), "timing" (0/1: per-kernel CUDA-event timing, see hpf_phase_ms). */
+/* Tunables (defaults are the measured ones, see the block at the top of hpf_engine.cu):
+ *   "panel_mb"  L2 panel size of the gathered factor side (takes effect at the next hpf_load_coo)
+ *   "chunk"     nnz walked by one lane group
+ *   "sweep"     0 two-pass segmented (default), 1 single-pass COO atomics, 2 fused user-major pass
+ *               (gathers + REDs), 3 bulk-copy (TMA) staged gathers, 4 fused item-major pass
+ *   "kernel"    two-pass kernel: 1 register gathers, 2 one-step register pipeline, 3 cp.async rings,
+ *               4 cp.async rings with vector-loaded triples (no broadcast shuffles; chunk % 4 == 0)
+ *   "lpg" / "minb" / "hint" / "block"   shape of the sweep kernel (lanes per row, resident CTAs per SM,
+ *               load hints, CTA size); 0 (-1 for hint) = measured default of the row class;
+ *               "strict"=1 makes an unknown shape an error instead of falling back to the default
+ *   "use_graph" 0/1: replay one CAVI iteration as a CUDA graph
+ *   "timing"    0/1: per-kernel CUDA-event timing, see hpf_phase_ms
+ * Environment: HPF_OPTIONS="name=value,..." applies these to every new engine; HPF_ROW_ALIGN=32|64|128|256
+ * sets the row alignment of the device matrices (default 128: whole cache lines). */
 int hpf_set_option(hpf_engine* h, const char* name, double value);
 
 /* ---- state ------------------------------------------------------------------------------ */
@@ -176,6 +187,10 @@ int hpf_launch_count(hpf_engine* h, int64_t* out);
 /* With option "timing"=1: accumulated device milliseconds of the four kernels of a full-batch
  * iteration since the option was set: [item-major pass, user-major pass, user update, item update]. */
 int hpf_phase_ms(hpf_engine* h, double out[4], int64_t* iterations);
+/* Human-readable resolved configuration (row stride, sweep mode, kernel and its shape, chunk, panels)
+ * for telemetry: what bench.py prints next to its numbers.  `lpg=0` means the generic shape of a row
+ * class without a measured table entry. */
+int hpf_describe(hpf_engine* h, char* buf, int64_t n);
 /* Leading dimension (padded k) of the engine's device matrices. */
 int hpf_ld(hpf_engine* h, int32_t* out);
 

@@ -430,7 +430,7 @@ def test_row_alignment_is_result_neutral(monkeypatch, golden_full, align, k, dty
     for _ in range(3):
         O.cavi_full_iteration(ref, g["Y"], g["ix_u"], g["ix_i"], **HYP)
     tol = 1e-11 if dtype == np.float64 else 3e-5
-    for sweep, kernel in ((0, 1), (0, 2), (0, 3), (1, 1), (2, 1), (4, 1)):
+    for sweep, kernel in ((0, 1), (0, 2), (0, 3), (0, 4), (1, 1), (2, 1), (4, 1)):
         out = _fit_gpu(g["Y"], g["ix_u"], g["ix_i"], 100, 100, k, 3, 123, dtype=dtype, sweep=sweep, kernel=kernel,
                        chunk=24, panel_mb=0.004)
         for key in STATE_KEYS:
@@ -466,11 +466,12 @@ def test_engine_options_from_environment(monkeypatch, golden_full):
                                      (50, np.float32), (50, np.float64), (64, np.float32), (100, np.float32),
                                      (128, np.float32), (128, np.float64), (200, np.float32), (400, np.float32)])
 @pytest.mark.parametrize("chunk", [5, 48, 64])
-@pytest.mark.parametrize("kernel", [2, 3])
+@pytest.mark.parametrize("kernel", [2, 3, 4])
 def test_pipelined_kernel_vs_oracle(k, dtype, chunk, kernel):
     """sweep_major_v2_kernel (option kernel=2: warp-uniform control flow, full-mask shuffles, one-step
-    register pipeline) and sweep_major_v3_kernel (kernel=3: cp.async rings in shared memory, three steps
-    ahead) on ragged data with empty rows, chunk lengths that are not multiples of the lane-group width,
+    register pipeline), sweep_major_v3_kernel (kernel=3: cp.async rings in shared memory, three steps
+    ahead) and sweep_major_v4_kernel (kernel=4: the same with vector-loaded triples; chunk=5 exercises its
+    fall-back to kernel 3) on ragged data with empty rows, chunk lengths that are not multiples of the lane-group width,
     several L2 panels: 2 iterations vs the fp64 oracle from the same start."""
     nU, nI, nnz = 500, 260, 9000
     u, i, y = O.synth_coo(nU - 40, nI - 30, nnz, seed=k + chunk)     # the last 40 users / 30 items have no data
@@ -484,7 +485,7 @@ def test_pipelined_kernel_vs_oracle(k, dtype, chunk, kernel):
         assert relerr(out[key], ref[key]) < tol, key
 
 
-@pytest.mark.parametrize("kernel", [2, 3])
+@pytest.mark.parametrize("kernel", [2, 3, 4])
 def test_pipelined_kernel_golden_trajectory(golden_full, kernel):
     """100 full-batch iterations of the README toy with the pipelined kernels vs the compiled reference."""
     g = golden_full

@@ -120,6 +120,7 @@ FUSED = dict(sweep=4, kernel=1, lpg=8, minb=3, hint=0, chunk=64)
 # (lpg, minb, hint, block) of the deep-pipeline kernel
 V3_CORE = [(8, 2, 0, 256), (8, 3, 0, 256), (8, 4, 0, 128), (8, 6, 0, 128), (4, 2, 0, 128), (4, 3, 0, 128),
            (16, 4, 0, 256), (16, 6, 0, 256)]
+V4_CORE = [(8, 2, 256), (8, 3, 256), (8, 4, 128), (4, 2, 128), (4, 3, 128), (16, 4, 256)]
 V2_CORE = [(8, 3, 0), (8, 2, 0), (8, 4, 0), (8, 5, 0), (8, 6, 0), (8, 3, 1), (16, 3, 0), (16, 4, 0), (16, 5, 0),
            (16, 6, 0), (4, 2, 0), (4, 3, 0), (16, 4, 1)]
 
@@ -130,7 +131,7 @@ def main():
     rec0, ref = s0.run(None, "classic", **CLASSIC)
     results.append(rec0)
     print("classic:", json.dumps(rec0), flush=True)
-    plan = [(128, 96.0), (128, 64.0), (128, 48.0), (128, 128.0), (32, 96.0), (128, 32.0)]
+    plan = [(128, 96.0), (128, 64.0), (128, 128.0), (128, 48.0)]
     if "--skip-v2" not in sys.argv:
         plan += [(128, 24.0), (32, 48.0), (32, 32.0)]
     for align, panel in plan:
@@ -148,6 +149,9 @@ def main():
         for lpg, minb, hint, block in V3_CORE:
             for chunk in (128, 256, 512):
                 results.append(st.run(ref, "v3", sweep=0, kernel=3, lpg=lpg, minb=minb, hint=hint, block=block, chunk=chunk))
+        for lpg, minb, block in V4_CORE:
+            for chunk in (128, 256, 512):
+                results.append(st.run(ref, "v4", sweep=0, kernel=4, lpg=lpg, minb=minb, hint=0, block=block, chunk=chunk))
         if st is not s0:
             st.close()
     s0.close()
@@ -155,7 +159,7 @@ def main():
     for r in top(results, 15):
         print(json.dumps(r), flush=True)
     # chunk / panel refinement around the best pipelined shape
-    lead = top(results, 1, lambda r: r.get("kernel") in (2, 3))
+    lead = top(results, 1, lambda r: r.get("kernel") in (2, 3, 4))
     if lead:
         b = lead[0]
         for panel in sorted({b["panel_mb"], 40.0, 56.0}):
@@ -173,7 +177,7 @@ def main():
     for r in h_top:
         print(json.dumps(r), flush=True)
     best["H_k50_alpha0.6"] = as_env(h_top[0])
-    for ver in (2, 3):
+    for ver in (2, 3, 4):
         lead_v = top(results, 1, lambda r: r.get("kernel") == ver)
         if lead_v:
             best["H_k50_alpha0.6_v%d" % ver] = as_env(lead_v[0])
@@ -220,6 +224,9 @@ def main():
                                      [(8, 2, 128), (8, 3, 128), (16, 2, 256), (16, 3, 256), (32, 4, 256), (32, 6, 256)]):
                 for chunk in (64, 256):
                     resk.append(st.run(refk, "v3-k%d" % k, sweep=0, kernel=3, lpg=lpg, minb=minb, hint=0, block=block, chunk=chunk))
+            for lpg, minb, block in ([(4, 2, 256), (4, 3, 256), (8, 4, 256)] if k == 30 else
+                                     [(8, 3, 128), (8, 2, 128), (16, 2, 256), (16, 3, 256)]):
+                resk.append(st.run(refk, "v4-k%d" % k, sweep=0, kernel=4, lpg=lpg, minb=minb, hint=0, block=block, chunk=256))
             st.close()
         print("== k=%d top 6 ==" % k)
         for r in top(resk, 6):
