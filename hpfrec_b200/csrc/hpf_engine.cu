@@ -479,10 +479,11 @@ int launch_sweep_v3(hpf_engine* h, const int* row, const int* col, const void* v
                     const void* xgat, void* acc) {
     auto kern = hpf::sweep_major_v3_kernel<real, LPG, VPL, MINB, HINT, BLOCK>;
     constexpr int smem = (BLOCK / 32) * 2 * 4 * VPL * 512;  // warps x (gather ring + own ring) x 4 slots x VPL x 512 B
-    static thread_local bool configured = false;  // per instantiation (function-local static of a template)
-    if (!configured) {
+    // the attribute is per device: remember it per (instantiation, device)
+    static thread_local bool configured[64] = {};
+    if (h->device >= 64 || !configured[h->device]) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+        if (h->device < 64) configured[h->device] = true;
     }
     const long long groups = (h->nnz + h->chunk - 1) / h->chunk;
     const long long threads = groups * LPG;
@@ -498,10 +499,10 @@ int launch_sweep_v4(hpf_engine* h, const int* row, const int* col, const void* v
                     const void* xgat, void* acc) {
     auto kern = hpf::sweep_major_v4_kernel<real, LPG, VPL, MINB, HINT, BLOCK>;
     constexpr int smem = (BLOCK / 32) * 2 * 4 * VPL * 512;
-    static thread_local bool configured = false;
-    if (!configured) {
+    static thread_local bool configured[64] = {};
+    if (h->device >= 64 || !configured[h->device]) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+        if (h->device < 64) configured[h->device] = true;
     }
     const long long groups = (h->nnz + h->chunk - 1) / h->chunk;
     const long long threads = groups * LPG;
