@@ -58,7 +58,7 @@ template <typename real, int LPG, int VPL>
 __global__ void __launch_bounds__(256)
 batch_prepare_kernel(int nrows, const int* __restrict__ rows, int ld, int k, const real* __restrict__ shp,
                      const real* __restrict__ rte, real* __restrict__ x, real* __restrict__ acc,
-                     int* __restrict__ stamp, int step) {
+                     real* __restrict__ direct, int* __restrict__ stamp, int step) {
     constexpr int EPV = Pack<real>::N;
     const int gl = (threadIdx.x & 31) % LPG;
     const unsigned gmask = group_mask<LPG>();
@@ -100,6 +100,7 @@ batch_prepare_kernel(int nrows, const int* __restrict__ rows, int ld, int k, con
             for (int e = 0; e < EPV; ++e) xn.v[e] = (off[v] + e < k) ? rexp(E[v].v[e] - m) : real(0);
             st_pack(x + (size_t)r * ld + off[v], xn);
             st_pack(acc + (size_t)r * ld + off[v], pack_zero<real>());
+            if (direct != nullptr) st_pack(direct + (size_t)r * ld + off[v], pack_zero<real>());
         }
         if (rows && gl == 0) stamp[r] = step;
     }
@@ -116,7 +117,7 @@ batch_prepare_kernel(int nrows, const int* __restrict__ rows, int ld, int k, con
 template <typename real, int LPG, int VPL>
 __global__ void __launch_bounds__(256)
 batch_major_kernel(int nrows, int ld, int k, const real* __restrict__ x, const real* __restrict__ acc,
-                   real* __restrict__ shp, real* __restrict__ rte, real* __restrict__ rate,
+                   const real* __restrict__ direct, real* __restrict__ shp, real* __restrict__ rte, real* __restrict__ rate,
                    const int* __restrict__ stamp, int step, const double* __restrict__ colsum_minor,
                    double* __restrict__ colsum_major, real prior, real shp_rate, real add_rate, real rho,
                    int blend_all) {
@@ -155,8 +156,9 @@ batch_major_kernel(int nrows, int ld, int k, const real* __restrict__ x, const r
             if (inb) {
                 const Pack<real> xv = ld_pack(x + (size_t)r * ld + off[v]);
                 const Pack<real> av = ld_pack(acc + (size_t)r * ld + off[v]);
+                const Pack<real> dv = direct ? ld_pack(direct + (size_t)r * ld + off[v]) : pack_zero<real>();
 #pragma unroll
-                for (int e = 0; e < EPV; ++e) sv.v[e] = (off[v] + e < k) ? fma(xv.v[e], av.v[e], prior) : real(0);
+                for (int e = 0; e < EPV; ++e) sv.v[e] = (off[v] + e < k) ? fma(xv.v[e], av.v[e], prior) + dv.v[e] : real(0);
                 st_pack(shp + (size_t)r * ld + off[v], sv);
             } else {
                 sv = ld_pack(shp + (size_t)r * ld + off[v]);
@@ -195,7 +197,7 @@ batch_major_kernel(int nrows, int ld, int k, const real* __restrict__ x, const r
 template <typename real, int LPG, int VPL>
 __global__ void __launch_bounds__(256)
 batch_minor_kernel(int nrows, const int* __restrict__ rows, int ld, int k, const real* __restrict__ x,
-                   const real* __restrict__ acc, real* __restrict__ shp, real* __restrict__ rte,
+                   const real* __restrict__ acc, const real* __restrict__ direct, real* __restrict__ shp, real* __restrict__ rte,
                    real* __restrict__ rate, const int* __restrict__ stamp, int step,
                    const double* __restrict__ colsum_major, real prior, real shp_rate, real add_rate,
                    real rho, real mult, int blend_all) {
@@ -233,10 +235,11 @@ batch_minor_kernel(int nrows, const int* __restrict__ rows, int ld, int k, const
             if (inb) {
                 const Pack<real> xv = ld_pack(x + (size_t)r * ld + off[v]);
                 const Pack<real> av = ld_pack(acc + (size_t)r * ld + off[v]);
+                const Pack<real> dv = direct ? ld_pack(direct + (size_t)r * ld + off[v]) : pack_zero<real>();
 #pragma unroll
                 for (int e = 0; e < EPV; ++e) {
                     if (off[v] + e < k) {
-                        sv.v[e] = rm * fma(xv.v[e], av.v[e], prior) + prev * sv.v[e];
+                        sv.v[e] = rm * (fma(xv.v[e], av.v[e], prior) + dv.v[e]) + prev * sv.v[e];
                         tv.v[e] = rho * (inv + other[v][e]) + prev * tv.v[e];
                     }
                 }

@@ -26,6 +26,7 @@ int batch_core(hpf_engine* h, const int* iu, const int* ii, const void* yv, int6
                double mult, bool blend_all, int step) {
     h->x_valid = false;  // per-row factors / accumulators are only valid for the batch rows from here on
     drop_graphs(h);
+    TRY(resolve_robust(h));
     return dispatch(h->rb, h->ld, [&](auto cfg) {
         using C = decltype(cfg);
         using real = typename C::real;
@@ -45,17 +46,19 @@ int batch_core(hpf_engine* h, const int* iu, const int* ii, const void* yv, int6
         const real add_k = (real)h->add_k, add_t = (real)h->add_t;
         const real srM = ub ? k_shp : t_shp, srm = ub ? t_shp : k_shp;
         const real addM = ub ? add_k : add_t, addm = ub ? add_t : add_k;
+        real* dirM = h->robust_on ? (real*)(ub ? h->dirU : h->dirI) : nullptr;
+        real* dirm = h->robust_on ? (real*)(ub ? h->dirI : h->dirU) : nullptr;
 
         // 1. softmax factors of the participating rows from the current state; zero their sums
         if (n_major_ids > 0) {
             hpf::batch_prepare_kernel<real, C::lpg, C::vpl><<<row_grid(n_major_ids, C::lpg), 256, 0, h->stream>>>(
-                (int)n_major_ids, list_major, ld, k, shpM, rteM, xM, accM, stampM, step);
+                (int)n_major_ids, list_major, ld, k, shpM, rteM, xM, accM, dirM, stampM, step);
             h->launches++;
         }
         const int64_t n_prep_minor = list_minor ? n_minor_ids : nm;
         if (n_prep_minor > 0) {
             hpf::batch_prepare_kernel<real, C::lpg, C::vpl><<<row_grid(n_prep_minor, C::lpg), 256, 0, h->stream>>>(
-                (int)n_prep_minor, list_minor, ld, k, shpm, rtem, xm, accm, stampm, step);
+                (int)n_prep_minor, list_minor, ld, k, shpm, rtem, xm, accm, dirm, stampm, step);
             h->launches++;
         }
         CKK();
@@ -74,7 +77,7 @@ int batch_core(hpf_engine* h, const int* iu, const int* ii, const void* yv, int6
         // 4. major side, all rows
         if (nM > 0) {
             hpf::batch_major_kernel<real, C::lpg, C::vpl><<<row_grid(nM, C::lpg), 256, smem, h->stream>>>(
-                (int)nM, ld, k, xM, accM, shpM, rteM, rateM, stampM, step, csm, csM, priorM, srM, addM, (real)rho,
+                (int)nM, ld, k, xM, accM, dirM, shpM, rteM, rateM, stampM, step, csm, csM, priorM, srM, addM, (real)rho,
                 blend_all ? 1 : 0);
             h->launches++;
             CKK();
@@ -84,7 +87,7 @@ int batch_core(hpf_engine* h, const int* iu, const int* ii, const void* yv, int6
         const int64_t nrows5 = walk_all ? nm : n_minor_ids;
         if (nrows5 > 0) {
             hpf::batch_minor_kernel<real, C::lpg, C::vpl><<<row_grid(nrows5, C::lpg), 256, 0, h->stream>>>(
-                (int)nrows5, walk_all ? nullptr : list_minor, ld, k, xm, accm, shpm, rtem, ratem, stampm, step, csM,
+                (int)nrows5, walk_all ? nullptr : list_minor, ld, k, xm, accm, dirm, shpm, rtem, ratem, stampm, step, csM,
                 priorm, srm, addm, (real)rho, (real)mult, blend_all ? 1 : 0);
             h->launches++;
             CKK();

@@ -4,7 +4,6 @@
 #include "../../include/hpf_b200.h"
 #include "hpf_kernels.cuh"
 #include "hpf_batch.cuh"
-#include "hpf_sweep_tma.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -55,37 +54,11 @@ int fail(int code, const char* fmt, ...) {
 constexpr int kDefaultRowAlign = 128;    // bytes; row stride rule in hpf_create (cache-line aligned rows)
 constexpr double kDefaultPanelMb = 96.0;  // L2 panel of the gathered factor side
 constexpr int kDefaultChunk = 256;       // nnz walked by one lane group
-constexpr int kDefaultSweepMode = 0;     // 0 two-pass, 2 fused user-major, 4 fused item-major
-
-struct Shape {
-    int lpg, minb, hint;  // lanes per row, resident CTAs per SM (launch bound), load hints (see sweep_major_kernel)
-};
-// fp32 row classes by capacity in 16-byte packs (8: k<=32, 16: k<=64, 32: k<=128); {0,0,0} = generic shape
-inline Shape default_shape(int packs, int real_bytes, bool fused) {
-    if (real_bytes == 4 && packs == 8) return fused ? Shape{8, 3, 0} : Shape{4, 2, 0};
-    if (real_bytes == 4 && packs == 16) return fused ? Shape{8, 3, 0} : Shape{4, 3, 1};
-    if (real_bytes == 4 && packs == 32) return fused ? Shape{16, 2, 0} : Shape{8, 4, 0};
-    return Shape{0, 0, 0};
-}
-// shapes of the pipelined two-pass kernel (option "kernel"=2)
-inline Shape default_shape_v2(int packs, int real_bytes) {
-    if (real_bytes == 4 && packs == 8) return Shape{8, 6, 0};
-    if (real_bytes == 4 && packs == 16) return Shape{8, 3, 0};
-    if (real_bytes == 4 && packs == 32) return Shape{16, 3, 0};
-    return Shape{0, 0, 0};
-}
-// shapes of the deep-pipeline two-pass kernel (option "kernel"=3)
-// (measured on the H data at k = 30 / 50 / 128: profiles/r01b_tune_v3b.jsonl)
-inline Shape default_shape_v3(int packs, int real_bytes) {
-    if (real_bytes == 4 && packs == 8) return Shape{4, 2, 0};
-    if (real_bytes == 4 && packs == 16) return Shape{8, 2, 0};
-    if (real_bytes == 4 && packs == 32) return Shape{8, 3, 0};
-    return Shape{0, 0, 0};
-}
-inline int default_block_v3(int packs, int real_bytes) {
-    return (real_bytes == 4 && packs == 32) ? 128 : 256;  // 4 packs per lane: 16 KB of rings per warp
-}
-constexpr int kDefaultKernel = 3;  // two-pass mode: 1 sweep_major_kernel, 2 sweep_major_v2_kernel, 3 sweep_major_v3_kernel
+constexpr int kMaxChunk = 4096;
+constexpr int kDefaultSweepMode = 0;     // 0 two-pass sweep_rows_kernel, 1 single-pass sweep_coo_kernel (cross-check)
+// The triple arrays of an ordering are padded with zero-count entries so that every lane group of a launch
+// owns a whole chunk and every warp whole groups (at most 8 groups per warp): < 9 chunks of padding.
+constexpr int kPadEntries = 9 * kMaxChunk;
 
 template <typename real_, int LPG, int VPL>
 struct Cfg {
@@ -250,10 +223,13 @@ struct hpf_engine {
     int chunk = kDefaultChunk;
     int sweep_mode = kDefaultSweepMode;
     int use_graph = 0;
-    int v_lpg = 0, v_minb = 0, v_hint = -1;  // sweep-kernel shape overrides (0 / -1 = default of the row class)
-    int v_block = 0;                         // CTA size of the deep-pipeline kernel (0 = default)
-    int strict = 0;                         // unknown shape = error instead of falling back to the default
-    int kernel_ver = kDefaultKernel;        // two-pass sweep kernel: 1 classic, 2 pipelined
+    int v_lpg = 0, v_block = 0;   // sweep-kernel shape overrides: lanes per row, CTA size (0 = default of the row class)
+    int v_hint = -1;              // L2 policies on the sweep's accesses (-1 default = on)
+    int v_fullrow = -1;           // copy whole row strides instead of zero-filling pad packs (-1 default = off)
+    int v_robust = -1;            // rescue path for underflowing normalisers: -1 auto (tiny shape priors), 0 off, 1 on
+    bool robust_on = false;       // resolved from v_robust and (a, c) when a step starts
+    void *dirU = nullptr, *dirI = nullptr;  // robust mode: phi sums that bypass the row factor (nU x ld, nI x ld)
+    int strict = 0;               // unknown shape = error instead of falling back to the default
     int64_t launches = 0;
     cudaGraphExec_t graph_lean = nullptr, graph_mat = nullptr;
     // optional per-kernel timing of full-batch iterations
@@ -397,10 +373,10 @@ int download_matrix(hpf_engine* h, const void* src, const void* denom, void* dst
 template <typename real>
 int build_order(hpf_engine* h, const int* major, const int* minor, const real* val, int64_t n,
                 int64_t n_major, int64_t n_minor, int** o_row, int** o_col, void** o_val) {
-    // 8 spare entries: the vector-load sweep reads whole groups of four triples (masked past the end)
-    CK(hpf_malloc(o_row, sizeof(int) * (size_t)(n + 8)));
-    CK(hpf_malloc(o_col, sizeof(int) * (size_t)(n + 8)));
-    CK(hpf_malloc(o_val, sizeof(real) * (size_t)(n + 8)));
+    // kPadEntries spare entries (zero counts, last row / column repeated): see sweep_rows_kernel
+    CK(hpf_malloc(o_row, sizeof(int) * (size_t)(n + kPadEntries)));
+    CK(hpf_malloc(o_col, sizeof(int) * (size_t)(n + kPadEntries)));
+    CK(hpf_malloc(o_val, sizeof(real) * (size_t)(n + kPadEntries)));
     if (n == 0) return HPF_OK;
     // panels: the gathered (minor) factor matrix is cut so one panel stays L2-resident
     const double minor_bytes = (double)n_minor * h->ld * h->rb;
@@ -435,7 +411,8 @@ int build_order(hpf_engine* h, const int* major, const int* minor, const real* v
     OCK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, p_in, p_out, (int)n, 0, end_bit, h->stream));
     if (rc == HPF_OK) {
         hpf::apply_order_kernel<real><<<nblk(n), 256, 0, h->stream>>>(k_out, p_out, n, span, minor, val, *o_row, *o_col, (real*)*o_val);
-        h->launches += 4;
+        hpf::pad_order_kernel<real><<<nblk(kPadEntries), 256, 0, h->stream>>>(*o_row, *o_col, (real*)*o_val, n, kPadEntries);
+        h->launches += 5;
     }
     OCK(cudaGetLastError());
     OCK(cudaStreamSynchronize(h->stream));
@@ -457,9 +434,17 @@ int launch_sweep_coo(hpf_engine* h, const int* iu, const int* ii, const void* va
     if (n == 0) return HPF_OK;
     const int chunk = 64;
     const long long groups = (n + chunk - 1) / chunk;
-    hpf::sweep_coo_kernel<real, C::lpg, C::vpl><<<nblk(groups * C::lpg), 256, 0, st>>>(
-        iu, ii, (const real*)val, n, chunk, (const real*)xu, (const real*)xi, (real*)accU, (real*)accI, ld,
-        (real*)phi, k);
+    if (h && h->robust_on) {  // rescue path: needs the materialised state of an engine
+        hpf::RescueArgs<real> rs{(const real*)h->Gshp, (const real*)h->Grte, (const real*)h->Lshp, (const real*)h->Lrte,
+                                 (real*)h->dirU, (real*)h->dirI, k};
+        hpf::sweep_coo_kernel<real, C::lpg, C::vpl, true><<<nblk(groups * C::lpg), 256, 0, st>>>(
+            iu, ii, (const real*)val, n, chunk, (const real*)xu, (const real*)xi, (real*)accU, (real*)accI, ld,
+            (real*)phi, k, rs);
+    } else {
+        hpf::sweep_coo_kernel<real, C::lpg, C::vpl, false><<<nblk(groups * C::lpg), 256, 0, st>>>(
+            iu, ii, (const real*)val, n, chunk, (const real*)xu, (const real*)xi, (real*)accU, (real*)accI, ld,
+            (real*)phi, k, hpf::RescueArgs<real>{});
+    }
     if (h) h->launches++;
     CKK();
     return HPF_OK;
@@ -491,12 +476,13 @@ int launch_update_rows(hpf_engine* h, bool users, bool mat) {
     const real prior = (real)(users ? h->a : h->c);
     const real shp_rate = (real)(users ? h->k_shp : h->t_shp);
     const real add_rate = (real)(users ? h->add_k : h->add_t);
+    real* direct = h->robust_on ? (real*)(users ? h->dirU : h->dirI) : nullptr;
     if (mat)
         hpf::update_rows_kernel<real, C::lpg, C::vpl, true><<<grid, 256, smem, h->stream>>>(
-            (int)n, h->ld, h->k, x, acc, shp, rte, rate, other, out, prior, shp_rate, add_rate);
+            (int)n, h->ld, h->k, x, acc, direct, shp, rte, rate, other, out, prior, shp_rate, add_rate);
     else
         hpf::update_rows_kernel<real, C::lpg, C::vpl, false><<<grid, 256, smem, h->stream>>>(
-            (int)n, h->ld, h->k, x, acc, shp, rte, rate, other, out, prior, shp_rate, add_rate);
+            (int)n, h->ld, h->k, x, acc, direct, shp, rte, rate, other, out, prior, shp_rate, add_rate);
     h->launches++;
     CKK();
     return HPF_OK;
@@ -537,49 +523,47 @@ void mark(hpf_engine* h, int which) {
     if (h->timing && h->ev[0]) cudaEventRecord(h->ev[which], h->stream);
 }
 
+// Resolves robust mode (rescue of underflowing normalisers, see sweep_rescue) and allocates its two
+// "direct" sum matrices on first use.  Auto rule: psi(x) ~ -1/x for small x, so a row's E[log] entries can
+// spread by ~1/prior; its exponentials keep full support in `real` while that spread stays below the
+// exponent range (87 for float, 708 for double).
+int resolve_robust(hpf_engine* h) {
+    const double lo = h->a < h->c ? h->a : h->c;
+    const bool want = h->v_robust >= 0 ? h->v_robust != 0 : lo < (h->rb == 4 ? 0.05 : 0.004);
+    if (want && !h->dirU) {
+        CK(hpf_malloc(&h->dirU, h->mat_bytes(h->nU > 0 ? h->nU : 1)));
+        CK(hpf_malloc(&h->dirI, h->mat_bytes(h->nI > 0 ? h->nI : 1)));
+        CK(cudaMemsetAsync(h->dirU, 0, h->mat_bytes(h->nU > 0 ? h->nU : 1), h->stream));
+        CK(cudaMemsetAsync(h->dirI, 0, h->mat_bytes(h->nI > 0 ? h->nI : 1), h->stream));
+    }
+    if (want != h->robust_on) drop_graphs(h);
+    h->robust_on = want;
+    return HPF_OK;
+}
+
 // sides: bit 0 = item-major pass (item-side sums), bit 1 = user-major pass (user-side sums).  The
-// single-pass modes (1: COO atomics, 2: fused) produce both sides in the "user" call.
+// single-pass cross-check mode (sweep=1: COO atomics) produces both sides in the "user" call.
 int do_sweep(hpf_engine* h, int sides = 3) {
     return dispatch(h->rb, h->ld, [&](auto cfg) {
         using C = decltype(cfg);
         if (sides & 1) mark(h, 0);
-        if (h->sweep_mode == 4) {
-            // one fused ITEM-major pass: item-side sums accumulate in registers (long segments, hot items
-            // cost nothing extra), every nnz pushes w * xi[i,:] into its user's sums with vector REDs
-            // (user degrees are small, so no address is hammered); both sides come out of the "item" call
-            if (sides & 1) {
-                TRY(launch_sweep_major<C>(h, h->B_row, h->B_col, h->B_val, h->xi, h->xu, h->accI, h->accU));
-                mark(h, 1);
-            }
-            if (sides & 2) mark(h, 2);
-            return HPF_OK;
-        }
-        if (h->sweep_mode == 1 || h->sweep_mode == 2) {
+        if (h->sweep_mode == 1) {
             if (sides & 1) mark(h, 1);
             if (sides & 2) {
-                if (h->sweep_mode == 1)
-                    TRY(launch_sweep_coo<C>(h, h->A_row, h->A_col, h->A_val, h->nnz, h->xu, h->xi, h->accU, h->accI,
-                                            h->ld, nullptr, h->k, h->stream));
-                else  // one fused user-major pass (gathers + REDs)
-                    TRY(launch_sweep_major<C>(h, h->A_row, h->A_col, h->A_val, h->xu, h->xi, h->accU, h->accI));
+                TRY(launch_sweep_coo<C>(h, h->A_row, h->A_col, h->A_val, h->nnz, h->xu, h->xi, h->accU, h->accI, h->ld,
+                                        nullptr, h->k, h->stream));
                 mark(h, 2);
             }
             return HPF_OK;
         }
         // item-major pass first: its output (item-side partial sums) is what a multi-GPU caller
-        // all-reduces, so the reduction can overlap the user-major pass
+        // exchanges, so the exchange can overlap the user-major pass
         if (sides & 1) {
-            if (h->sweep_mode == 3)  // staged gathers: cp.async.bulk + mbarrier ring
-                TRY(launch_sweep_tma<C>(h, h->B_row, h->B_col, h->B_val, h->xi, h->xu, h->accI));
-            else
-                TRY(launch_sweep_major<C>(h, h->B_row, h->B_col, h->B_val, h->xi, h->xu, h->accI));
+            TRY(launch_sweep_major<C>(h, h->B_row, h->B_col, h->B_val, h->xi, h->xu, h->accI, false));
             mark(h, 1);
         }
         if (sides & 2) {
-            if (h->sweep_mode == 3)
-                TRY(launch_sweep_tma<C>(h, h->A_row, h->A_col, h->A_val, h->xu, h->xi, h->accU));
-            else
-                TRY(launch_sweep_major<C>(h, h->A_row, h->A_col, h->A_val, h->xu, h->xi, h->accU));
+            TRY(launch_sweep_major<C>(h, h->A_row, h->A_col, h->A_val, h->xu, h->xi, h->accU, true));
             mark(h, 2);
         }
         return HPF_OK;
@@ -596,6 +580,7 @@ int do_update(hpf_engine* h, bool users, bool mat) {
 }
 
 int one_iteration(hpf_engine* h, bool mat) {
+    if (h->robust_on) mat = true;  // the rescue path recomputes E[log] from the materialised state
     TRY(do_sweep(h));
     TRY(do_update(h, true, mat));
     mark(h, 3);
@@ -765,7 +750,7 @@ int hpf_destroy(hpf_engine* h) {
     for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
     h->ipc_opened.clear();
     void* ptrs[] = {h->Gshp, h->Grte, h->Lshp, h->Lrte, h->krte, h->trte, h->xu, h->xi, h->accU, h->accI, h->Tsum, h->Bsum, h->stamp_u, h->stamp_i,
-                    h->bt_major, h->bt_minor, h->bt_cnt, h->bt_off, h->bt_ids, h->bt_val, h->bt_scan_tmp};
+                    h->bt_major, h->bt_minor, h->bt_cnt, h->bt_off, h->bt_ids, h->bt_val, h->bt_scan_tmp, h->dirU, h->dirI};
     for (void* p : ptrs) hpf_free(p);
     delete h;
     return HPF_OK;
@@ -821,29 +806,24 @@ int hpf_set_option(hpf_engine* h, const char* name, double value) {
         if (!(value > 0)) return fail(HPF_EINVAL, "panel_mb must be > 0");
         h->panel_mb = value;  // takes effect at the next hpf_load_coo
     } else if (!strcmp(name, "chunk")) {
-        if (value < 1 || value > (1 << 20)) return fail(HPF_EINVAL, "chunk out of range");
+        if (value < 32 || value > kMaxChunk || ((int)value % 32) != 0)
+            return fail(HPF_EINVAL, "chunk must be a multiple of 32 in [32, %d]", kMaxChunk);
         h->chunk = (int)value;
         drop_graphs(h);
     } else if (!strcmp(name, "sweep")) {
-        if (value < 0 || value > 4) return fail(HPF_EINVAL, "sweep must be 0..4");
+        if (value != 0 && value != 1) return fail(HPF_EINVAL, "sweep must be 0 (two-pass) or 1 (single-pass COO cross-check)");
         h->sweep_mode = (int)value;
         drop_graphs(h);
-    } else if (!strcmp(name, "lpg") || !strcmp(name, "minb") || !strcmp(name, "hint")) {
-        if (value < -1 || value > 64) return fail(HPF_EINVAL, "%s out of range", name);
-        if (!strcmp(name, "lpg")) h->v_lpg = value > 0 ? (int)value : 0;      // 0 = default of the row class
-        if (!strcmp(name, "minb")) h->v_minb = value > 0 ? (int)value : 0;    // 0 = default
-        if (!strcmp(name, "hint")) h->v_hint = (int)value;                    // -1 = default
+    } else if (!strcmp(name, "lpg") || !strcmp(name, "block")) {
+        if (value < 0 || value > 1024) return fail(HPF_EINVAL, "%s out of range", name);
+        if (!strcmp(name, "lpg")) h->v_lpg = (int)value;      // 0 = default of the row class
+        if (!strcmp(name, "block")) h->v_block = (int)value;  // 0 = default
         drop_graphs(h);
-    } else if (!strcmp(name, "block")) {
-        if (value != 0 && value != 128 && value != 256) return fail(HPF_EINVAL, "block must be 0 (default), 128 or 256");
-        h->v_block = (int)value;
-        drop_graphs(h);
-    } else if (!strcmp(name, "unroll")) {
-        if (value != 0 && value != 1) return fail(HPF_EINVAL, "unrolled sweep shapes were measured slower and removed (unroll must be 1)");
-    } else if (!strcmp(name, "kernel")) {
-        if (value != 1 && value != 2 && value != 3 && value != 4)
-            return fail(HPF_EINVAL, "kernel must be 1 (classic), 2 (register pipeline), 3 (cp.async pipeline) or 4 (cp.async pipeline, vector-loaded triples)");
-        h->kernel_ver = (int)value;
+    } else if (!strcmp(name, "hint") || !strcmp(name, "fullrow") || !strcmp(name, "robust")) {
+        if (value != -1 && value != 0 && value != 1) return fail(HPF_EINVAL, "%s must be -1 (default), 0 or 1", name);
+        if (!strcmp(name, "hint")) h->v_hint = (int)value;
+        if (!strcmp(name, "fullrow")) h->v_fullrow = (int)value;
+        if (!strcmp(name, "robust")) h->v_robust = (int)value;
         drop_graphs(h);
     } else if (!strcmp(name, "strict")) {
         h->strict = (int)value;
@@ -986,6 +966,7 @@ int hpf_sweep(hpf_engine* h) {
     if (!h) return fail(HPF_EINVAL, "engine is NULL");
     if (!h->data_loaded) return fail(HPF_ESTATE, "no data loaded (call hpf_load_coo first)");
     DeviceGuard guard(h->device);
+    TRY(resolve_robust(h));
     TRY(ensure_x(h));
     return do_sweep(h);
 }
@@ -995,6 +976,8 @@ int hpf_sweep_side(hpf_engine* h, int32_t side) {
     if (side != 0 && side != 1) return fail(HPF_EINVAL, "side must be 0 (items) or 1 (users)");
     if (!h->data_loaded) return fail(HPF_ESTATE, "no data loaded (call hpf_load_coo first)");
     DeviceGuard guard(h->device);
+    TRY(resolve_robust(h));
+    if (h->robust_on) return fail(HPF_EINVAL, "robust mode (tiny shape priors) is not available for sharded sweeps");
     TRY(ensure_x(h));
     return do_sweep(h, side == 0 ? 1 : 2);
 }
@@ -1036,6 +1019,7 @@ int hpf_step_full(hpf_engine* h, int32_t niter) {
     if (!h->state_loaded) return fail(HPF_ESTATE, "no state loaded (call hpf_load_state first)");
     if (niter == 0) return HPF_OK;
     DeviceGuard guard(h->device);
+    TRY(resolve_robust(h));
     TRY(ensure_x(h));
     h->mat_valid = false;
     const bool graph = h->use_graph && !h->timing && h->stream != nullptr && h->stream != cudaStreamLegacy;
@@ -1174,29 +1158,21 @@ int hpf_describe(hpf_engine* h, char* buf, int64_t n) {
     const int packs_row = h->ld * h->rb / 16;
     int cls = 8;
     while (cls < packs_row) cls *= 2;
-    const bool fused = h->sweep_mode == 2 || h->sweep_mode == 4;
-    Shape d = default_shape(cls, h->rb, fused);
-    const char* kern = fused ? "sweep_major_kernel<FUSE>" : "sweep_major_kernel";
-    int block = 256;
-    if (!fused && h->sweep_mode == 0 && h->kernel_ver == 2) {
-        d = default_shape_v2(cls, h->rb);
-        kern = "sweep_major_v2_kernel";
-    } else if (!fused && h->sweep_mode == 0 && (h->kernel_ver == 3 || h->kernel_ver == 4)) {
-        d = default_shape_v3(cls, h->rb);
-        kern = (h->kernel_ver == 4 && h->chunk % 4 == 0) ? "sweep_major_v4_kernel" : "sweep_major_v3_kernel";
-        block = h->v_block ? h->v_block : default_block_v3(cls, h->rb);
-    } else if (h->sweep_mode == 1) {
-        kern = "sweep_coo_kernel";
-    } else if (h->sweep_mode == 3) {
-        kern = "sweep_tma_kernel";
+    const RowsShape d = default_rows_shape(cls, h->rb);
+    int lpg = h->v_lpg ? h->v_lpg : d.lpg, block = h->v_block ? h->v_block : d.block;
+    if (lpg == 0) {  // generic shape: the row class's lane-group width, 128-thread CTAs
+        lpg = cls <= 16 ? 8 : (cls <= 32 ? 16 : 32);
+        block = 128;
     }
-    const int lpg = h->v_lpg ? h->v_lpg : d.lpg, minb = h->v_minb ? h->v_minb : d.minb;
-    const int hint = h->v_hint >= 0 ? h->v_hint : d.hint;
+    const int hint = h->v_hint >= 0 ? h->v_hint : 1;
+    const int fullrow = (h->v_fullrow > 0 && h->ld * h->rb / 16 == cls) ? 1 : 0;
+    const double lo = h->a < h->c ? h->a : h->c;
+    const int robust = h->v_robust >= 0 ? h->v_robust : (lo < (h->rb == 4 ? 0.05 : 0.004) ? 1 : 0);
     snprintf(buf, (size_t)n,
-             "real_bytes=%d k=%d kw=%d ld=%d sweep=%d kernel=%s lpg=%d minb=%d hint=%d block=%d chunk=%d panel_mb=%g "
-             "panels_user_major=%d panels_item_major=%d launches_per_iteration=%d",
-             h->rb, h->k, h->kw, h->ld, h->sweep_mode, kern, lpg, minb, hint, block, h->chunk, h->panel_mb, h->panelsA,
-             h->panelsB, (h->sweep_mode == 0 || h->sweep_mode == 3) ? 4 : 3);
+             "real_bytes=%d k=%d kw=%d ld=%d sweep=%d kernel=%s lpg=%d block=%d hint=%d fullrow=%d robust=%d chunk=%d "
+             "panel_mb=%g panels_user_major=%d panels_item_major=%d launches_per_iteration=%d",
+             h->rb, h->k, h->kw, h->ld, h->sweep_mode, h->sweep_mode == 1 ? "sweep_coo_kernel" : "sweep_rows_kernel", lpg,
+             block, hint, fullrow, robust, h->chunk, h->panel_mb, h->panelsA, h->panelsB, h->sweep_mode == 0 ? 4 : 3);
     return HPF_OK;
 }
 
@@ -1337,6 +1313,9 @@ int hpf_update_shapes(int32_t real_bytes, int32_t index_bytes, int32_t device, v
         // rate vectors are not touched by these two loops; upload dummies
         std::vector<char> ones((size_t)(nU > nI ? nU : nI) * real_bytes + 8, 0);
         if ((rc = hpf_load_state(h, G_sh, G_rt, L_sh, L_rt, ones.data(), ones.data())) != HPF_OK) break;
+        h->a = a;
+        h->c = c;
+        if ((rc = resolve_robust(h)) != HPF_OK) break;
         if ((rc = ensure_x(h)) != HPF_OK) break;
         if (hpf_malloc(&u32, 4 * n1) != cudaSuccess || hpf_malloc(&i32, 4 * n1) != cudaSuccess || hpf_malloc(&d_bad, 4) != cudaSuccess) {
             rc = fail(HPF_ENOMEM, "device allocation failed");
@@ -1362,8 +1341,8 @@ int hpf_update_shapes(int32_t real_bytes, int32_t index_bytes, int32_t device, v
             using C = decltype(cfg);
             using real = typename C::real;
             TRY(launch_sweep_coo<C>(h, u32, i32, yv, nY, h->xu, h->xi, h->accU, h->accI, h->ld, phi_target, k, h->stream));
-            if (nU > 0) hpf::finish_shapes_kernel<real><<<nblk(nU * h->ld), 256, 0, h->stream>>>(nU * h->ld, (const real*)h->xu, (const real*)h->accU, (real*)h->Gshp, (real)a);
-            if (nI > 0) hpf::finish_shapes_kernel<real><<<nblk(nI * h->ld), 256, 0, h->stream>>>(nI * h->ld, (const real*)h->xi, (const real*)h->accI, (real*)h->Lshp, (real)c);
+            if (nU > 0) hpf::finish_shapes_kernel<real><<<nblk(nU * h->ld), 256, 0, h->stream>>>(nU * h->ld, (const real*)h->xu, (const real*)h->accU, (const real*)(h->robust_on ? h->dirU : nullptr), (real*)h->Gshp, (real)a);
+            if (nI > 0) hpf::finish_shapes_kernel<real><<<nblk(nI * h->ld), 256, 0, h->stream>>>(nI * h->ld, (const real*)h->xi, (const real*)h->accI, (const real*)(h->robust_on ? h->dirI : nullptr), (real*)h->Lshp, (real)c);
             CKK();
             return HPF_OK;
         });

@@ -22,10 +22,12 @@ namespace hpf {
 //   rate[r] = add_rate + sum_j E[x]              pxi:258 / 259
 //   x    = exp(psi(shp) - log(rte) - rowmax)     the per-row factor of next iteration's update_phi
 // MAT=true also stores shp and rte (needed for export / minibatch steps); lean iterations skip that.
+// `direct` (robust mode, else NULL): phi sums of the nnz the sweep's rescue path handled, added to the
+// shape as they are (not scaled by x) and re-zeroed.
 // =============================================================================================
 template <typename real, int LPG, int VPL, bool MAT>
 __global__ void __launch_bounds__(256)
-update_rows_kernel(int nrows, int ld, int k, real* __restrict__ x, real* __restrict__ acc,
+update_rows_kernel(int nrows, int ld, int k, real* __restrict__ x, real* __restrict__ acc, real* __restrict__ direct,
                    real* __restrict__ shp_out, real* __restrict__ rte_out, real* __restrict__ rate,
                    const double* __restrict__ colsum_other, double* __restrict__ colsum_out,
                    real prior, real shp_rate, real add_rate) {
@@ -66,10 +68,15 @@ update_rows_kernel(int nrows, int ld, int k, real* __restrict__ x, real* __restr
             if (!act[v]) continue;
             const Pack<real> xv = ld_pack(x + (size_t)r * ld + off[v]);
             const Pack<real> av = ld_pack(acc + (size_t)r * ld + off[v]);
+            Pack<real> dv = pack_zero<real>();
+            if (direct != nullptr) {
+                dv = ld_pack(direct + (size_t)r * ld + off[v]);
+                st_pack(direct + (size_t)r * ld + off[v], pack_zero<real>());
+            }
 #pragma unroll
             for (int e = 0; e < EPV; ++e) {
                 const bool real_col = off[v] + e < k;
-                const real s_ = fma(xv.v[e], av.v[e], prior);
+                const real s_ = fma(xv.v[e], av.v[e], prior) + dv.v[e];
                 const real t_ = inv + other[v][e];
                 shp[v].v[e] = real_col ? s_ : real(0);
                 rte[v].v[e] = real_col ? t_ : real(1);
@@ -309,12 +316,12 @@ rows_to_x_kernel(int nrows, const int* __restrict__ rows, int ld, int k, const r
     }
 }
 
-// shp = prior + x * acc for every row (finishes a stand-alone hpf_update_shapes call)
+// shp = prior + x * acc (+ direct) for every row (finishes a stand-alone hpf_update_shapes call)
 template <typename real>
-__global__ void finish_shapes_kernel(long long n_elems, const real* __restrict__ x,
-                                     const real* __restrict__ acc, real* __restrict__ shp, real prior) {
+__global__ void finish_shapes_kernel(long long n_elems, const real* __restrict__ x, const real* __restrict__ acc,
+                                     const real* __restrict__ direct, real* __restrict__ shp, real prior) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_elems) shp[i] = fma(x[i], acc[i], prior);
+    if (i < n_elems) shp[i] = fma(x[i], acc[i], prior) + (direct ? direct[i] : real(0));
 }
 
 // =============================================================================================
@@ -353,6 +360,18 @@ __global__ void apply_order_kernel(const unsigned long long* __restrict__ keys_s
     out_row[i] = (int)(keys_sorted[i] % major_span);
     out_col[i] = minor[p];
     out_val[i] = val[p];
+}
+
+// zero-count padding behind the n sorted triples of an ordering: repeats the last (row, col) so that the
+// sweep sees neither a row change nor an invalid address, and contributes exactly 0
+template <typename real>
+__global__ void pad_order_kernel(int* __restrict__ row, int* __restrict__ col, real* __restrict__ val, long long n,
+                                 int pad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pad) return;
+    row[n + i] = row[n - 1];
+    col[n + i] = col[n - 1];
+    val[n + i] = real(0);
 }
 
 // strided copy helpers between packed (n x k) caller layout and padded (n x ld) engine layout

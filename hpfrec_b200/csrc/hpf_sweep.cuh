@@ -1,611 +1,272 @@
-// Sweep kernels of the HPF coordinate-ascent engine (sm_100a): the per-nnz part of one CAVI iteration,
-// replacing update_phi (pxi:551) + update_G_n_L_sh (pxi:613) of david-cortes/hpfrec without ever
-// materialising phi.  Four generations of the two-pass kernel are kept selectable (option "kernel"):
-// each one's header says what the previous one was measured to be bound by.  See hpf_kernels.cuh for the
-// identity that turns the per-nnz softmax into per-row factors, DESIGN.md section 5 for the numbers.
+// Sweep kernels of the HPF coordinate-ascent engine (sm_100a): sweep_rows_kernel (full-batch CAVI, one
+// direction per launch) and sweep_coo_kernel (minibatches, any nnz order, both directions at once).
+//
+// sweep_rows_kernel: one launch is one DIRECTION of the per-nnz part of a CAVI iteration: it replaces update_phi
+// (pxi:551-591) + update_G_n_L_sh (pxi:613-621) of david-cortes/hpfrec for ONE of the two shape
+// matrices, without materialising phi (hpf_kernels.cuh explains the per-row factorisation):
+//
+//       acc[r, :] += sum_{n : row(n) = r}  (Y[n] / dot(xown[r, :], xgat[col(n), :])) * xgat[col(n), :]
+//
+// The triples are sorted by (L2 panel of col, row).  LPG consecutive lanes form a lane group that walks
+// one contiguous chunk of the list; the row a group currently owns lives in registers together with
+// its running sum, which is flushed with one vector RED per 16-byte pack when the row id changes.
+//
+// What this revision changes against the round-1 kernel (17 issued instructions per nnz, issue-bound):
+//   * the triples of a batch go through shared memory (one STS.128 per lane per batch), so a step reads
+//     them with two broadcast LDS.64 instead of three SHFL plus register queues;
+//   * the arrays are padded by the host to whole chunks with zero-count entries, so the loop has no
+//     "past the end" predicates at all;
+//   * packs beyond the row's active width are handled by cp.async's src-size operand (0 = zero-fill,
+//     no global read) instead of per-lane predicates and duplicated address chains, or -- FULLROW --
+//     by copying the zero padding of a full-stride row;
+//   * the dot product and the accumulation use the packed fp32 FMA of sm_100 (FFMA2: fma.rn.f32x2),
+//     halving the FP32 instruction count;
+//   * every global access carries an L2 policy: gathered rows evict_last (they are the panel that has
+//     to stay resident), the streamed triples / own rows / REDs evict_first.
+// ROBUST adds the rescue path for normalisers that underflow with tiny shape hyper-parameters
+// (see sweep_rescue below).
 #pragma once
 #include "hpf_device.cuh"
 
 namespace hpf {
 
-// =============================================================================================
-// K2  cavi sweep, one direction ("major" side = rows owned by consecutive nnz, "minor" = gathered)
-//     replaces update_phi (pxi:551) + update_G_n_L_sh (pxi:613) for ONE of the two shape matrices.
-//     nnz are sorted by (L2 panel of the minor id, major id); every lane group walks a contiguous
-//     chunk, keeps the major row's x and the running sum in registers, gathers the minor row with
-//     128-bit loads, reduces the normaliser with shuffles inside the group, and flushes the running
-//     sum with one vector RED per pack when the major id changes (so atomics happen once per
-//     (row, chunk) segment, not once per nnz).
-//       acc[r, :] += sum_{n in segment} (Y[n] / dot(xown[r], xgat[c_n])) * xgat[c_n, :]
-// =============================================================================================
-//     HINT: 0 plain loads; 1 triples evict_first + gathers evict_last; 2 triples evict_first only;
-//     3 triples evict_first + gathers L1::no_allocate.
-//     FUSE=1 ("one-pass" mode): the same walk also pushes w_n * xown[r,:] into the MINOR side's sums
-//     with one vector RED per pack per nnz, so a single user-major pass produces both shape matrices;
-//     gathers ride the L2->SM response path and the REDs the SM->L2 request path.
-template <typename real, int LPG, int VPL, int UNROLL, int MINB, int HINT, int FUSE>
-__global__ void __launch_bounds__(256, MINB)
-sweep_major_kernel(const int* __restrict__ row, const int* __restrict__ col,
-                   const real* __restrict__ val, long long nnz, int chunk,
-                   const real* __restrict__ xown, const real* __restrict__ xgat,
-                   real* __restrict__ acc, real* __restrict__ acc_minor, int ld, int kw) {
+// ---- small device helpers local to the sweep --------------------------------------------------------
+__device__ __forceinline__ void cp_async16_pol(uint32_t dst, const void* src, uint64_t pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(pol) : "memory");
+}
+// src_size = 16 copies, src_size = 0 zero-fills the 16 bytes without reading global memory
+__device__ __forceinline__ void cp_async16_sz_pol(uint32_t dst, const void* src, uint32_t src_size, uint64_t pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(dst), "l"(src), "r"(src_size), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async16_sz(uint32_t dst, const void* src, uint32_t src_size) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_size) : "memory");
+}
+__device__ __forceinline__ void lds64(uint32_t addr, int& a, int& b) {
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr));
+}
+__device__ __forceinline__ void red_add_pack_pol(float* p, const Pack<float>& r, uint64_t pol) {
+    asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]),
+                 "f"(r.v[2]), "f"(r.v[3]), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void red_add_pack_pol(double* p, const Pack<double>& r, uint64_t pol) {
+    asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(r.v[0]), "l"(pol) : "memory");
+    asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p + 1), "d"(r.v[1]), "l"(pol) : "memory");
+}
+
+// two-lane partial dot product / scaled accumulation of one pack; float uses FFMA2 (fma.rn.f32x2)
+struct Dot2f {
+    float2 d;
+    __device__ __forceinline__ Dot2f() : d(make_float2(0.f, 0.f)) {}
+    __device__ __forceinline__ void add(const Pack<float>& a, const Pack<float>& b) {
+        d = __ffma2_rn(make_float2(a.v[0], a.v[1]), make_float2(b.v[0], b.v[1]), d);
+        d = __ffma2_rn(make_float2(a.v[2], a.v[3]), make_float2(b.v[2], b.v[3]), d);
+    }
+    __device__ __forceinline__ float total() const { return d.x + d.y; }
+};
+struct Dot2d {
+    double d0, d1;
+    __device__ __forceinline__ Dot2d() : d0(0.0), d1(0.0) {}
+    __device__ __forceinline__ void add(const Pack<double>& a, const Pack<double>& b) {
+        d0 = fma(a.v[0], b.v[0], d0);
+        d1 = fma(a.v[1], b.v[1], d1);
+    }
+    __device__ __forceinline__ double total() const { return d0 + d1; }
+};
+template <typename real> struct DotOf;
+template <> struct DotOf<float> { using type = Dot2f; };
+template <> struct DotOf<double> { using type = Dot2d; };
+
+__device__ __forceinline__ void axpy_pack(Pack<float>& s, float w, const Pack<float>& g) {
+    const float2 ww = make_float2(w, w);
+    const float2 lo = __ffma2_rn(ww, make_float2(g.v[0], g.v[1]), make_float2(s.v[0], s.v[1]));
+    const float2 hi = __ffma2_rn(ww, make_float2(g.v[2], g.v[3]), make_float2(s.v[2], s.v[3]));
+    s.v[0] = lo.x; s.v[1] = lo.y; s.v[2] = hi.x; s.v[3] = hi.y;
+}
+__device__ __forceinline__ void axpy_pack(Pack<double>& s, double w, const Pack<double>& g) {
+    s.v[0] = fma(w, g.v[0], s.v[0]);
+    s.v[1] = fma(w, g.v[1], s.v[1]);
+}
+
+// normaliser below which the per-row factorisation is no longer trusted (ROBUST instantiations only):
+// every x is exp(E - rowmax) <= 1 with one entry equal to 1 per row, so a normaliser this small means
+// the two rows' exponentials have (almost) disjoint support in `real`
+template <typename real> __device__ __forceinline__ real rescue_threshold();
+template <> __device__ __forceinline__ float rescue_threshold<float>() { return 1e-25f; }
+template <> __device__ __forceinline__ double rescue_threshold<double>() { return 1e-250; }
+
+// Materialised state the rescue path recomputes E[log] from, and where it puts its result: the
+// multinomial of the reference itself, phi[n, :] = Y[n] * softmax(Eown + Egat) with the JOINT maximum
+// subtracted (pxi:560-577), added to `direct` -- a sum the row update adds to the shape without
+// multiplying it by the row factor x (which is exactly what underflowed).
+template <typename real>
+struct RescueArgs {
+    const real* shp_own;
+    const real* rte_own;
+    const real* shp_gat;
+    const real* rte_gat;
+    real* direct_own;
+    real* direct_gat;  // NULL in the two-pass sweep (the other pass owns that side)
+    int k;
+};
+
+template <typename real, int LPG, int VPL>
+__device__ __noinline__ void sweep_rescue(const RescueArgs<real>& ra, int r_own, int c_gat, real y, int ld, int gl,
+                                          real* phi_row = nullptr) {
     constexpr int EPV = Pack<real>::N;
-    static_assert(LPG % UNROLL == 0, "UNROLL must divide LPG");
-    const int gl = (threadIdx.x & 31) % LPG;
-    const long long group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPG;
-    const long long beg = group * (long long)chunk;
-    if (beg >= nnz) return;  // whole groups leave together; shuffles below use the group mask
-    const long long end = (beg + chunk < nnz) ? beg + chunk : nnz;
     const unsigned gmask = group_mask<LPG>();
-    uint64_t pol_keep = 0, pol_stream = 0;
-    if (HINT) {
-        pol_keep = l2_policy_keep();
-        pol_stream = l2_policy_stream();
-    }
-
-    int off[VPL];
-    bool act[VPL];
+    real l[VPL][EPV];
+    real m = -INFINITY;
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
-        off[v] = (gl + LPG * v) * EPV;
-        act[v] = off[v] < kw;  // packs holding at least one real column (stride ld may be wider)
+        const int off = (gl + LPG * v) * EPV;
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) {
+            const int j = off + e;
+            real lj = -INFINITY;
+            if (j < ra.k) {
+                const size_t ao = (size_t)r_own * ld + j, ag = (size_t)c_gat * ld + j;
+                lj = elog(ra.shp_own[ao], ra.rte_own[ao]) + elog(ra.shp_gat[ag], ra.rte_gat[ag]);
+            }
+            l[v][e] = lj;
+            m = lj > m ? lj : m;
+        }
     }
-    Pack<real> own[VPL], sum[VPL];
+    m = group_max<LPG>(m, gmask);
+    real s = real(0);
+#pragma unroll
+    for (int v = 0; v < VPL; ++v)
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) {
+            l[v][e] = rexp(l[v][e] - m);  // exp(-inf) = 0 for pad columns
+            s += l[v][e];
+        }
+    s = group_sum<LPG>(s, gmask);
+    const real w = y / s;
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
-        own[v] = pack_zero<real>();
-        sum[v] = pack_zero<real>();
-    }
-    int cur = -1;
-
-    // coalesced fetch of LPG triples (one per lane), software-pipelined one batch ahead
-    int r = -1, c = 0;
-    real y = real(0);
-    if (beg + gl < end) {
-        if (HINT) {
-            r = ldg_stream(row + beg + gl, pol_stream);
-            c = ldg_stream(col + beg + gl, pol_stream);
-            y = ldg_stream(val + beg + gl, pol_stream);
-        } else {
-            r = __ldg(row + beg + gl);
-            c = __ldg(col + beg + gl);
-            y = __ldg(val + beg + gl);
-        }
-    }
-    for (long long base = beg; base < end; base += LPG) {
-        int rn = -1, cn = 0;
-        real yn = real(0);
-        const long long nidx = base + LPG + gl;
-        if (nidx < end) {
-            if (HINT) {
-                rn = ldg_stream(row + nidx, pol_stream);
-                cn = ldg_stream(col + nidx, pol_stream);
-                yn = ldg_stream(val + nidx, pol_stream);
-            } else {
-                rn = __ldg(row + nidx);
-                cn = __ldg(col + nidx);
-                yn = __ldg(val + nidx);
+        const int off = (gl + LPG * v) * EPV;
+#pragma unroll
+        for (int e = 0; e < EPV; ++e)
+            if (off + e < ra.k) {
+                atomicAdd(ra.direct_own + (size_t)r_own * ld + off + e, w * l[v][e]);
+                if (ra.direct_gat != nullptr) atomicAdd(ra.direct_gat + (size_t)c_gat * ld + off + e, w * l[v][e]);
+                if (phi_row != nullptr) phi_row[off + e] = w * l[v][e];
             }
-        }
-#pragma unroll
-        for (int t0 = 0; t0 < LPG; t0 += UNROLL) {
-            if (base + t0 >= end) break;  // uniform inside the group
-            Pack<real> g[UNROLL][VPL];
-            int rr[UNROLL], ccs[UNROLL];
-            real yy[UNROLL];
-#pragma unroll
-            for (int q = 0; q < UNROLL; ++q) {
-                const int cc = __shfl_sync(gmask, c, t0 + q, LPG);
-                ccs[q] = cc;
-                rr[q] = __shfl_sync(gmask, r, t0 + q, LPG);
-                yy[q] = __shfl_sync(gmask, y, t0 + q, LPG);
-                const real* src = xgat + (size_t)cc * ld;
-#pragma unroll
-                for (int v = 0; v < VPL; ++v) {
-                    if (HINT == 1)
-                        g[q][v] = act[v] ? ldg_pack_hint(src + off[v], pol_keep) : pack_zero<real>();
-                    else if (HINT == 3)
-                        g[q][v] = act[v] ? ldg_pack_noalloc(src + off[v]) : pack_zero<real>();
-                    else
-                        g[q][v] = act[v] ? ldg_pack(src + off[v]) : pack_zero<real>();
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < UNROLL; ++q) {
-                if (rr[q] < 0) continue;  // past the end of the chunk (uniform inside the group)
-                if (rr[q] != cur) {
-                    if (cur >= 0) {
-#pragma unroll
-                        for (int v = 0; v < VPL; ++v)
-                            if (act[v]) red_add_pack(acc + (size_t)cur * ld + off[v], sum[v]);
-                    }
-                    cur = rr[q];
-#pragma unroll
-                    for (int v = 0; v < VPL; ++v) {
-                        own[v] = act[v] ? ldg_pack(xown + (size_t)cur * ld + off[v]) : pack_zero<real>();
-                        sum[v] = pack_zero<real>();
-                    }
-                }
-                real s = real(0);
-#pragma unroll
-                for (int v = 0; v < VPL; ++v)
-#pragma unroll
-                    for (int e = 0; e < EPV; ++e) s = fma(own[v].v[e], g[q][v].v[e], s);
-                s = group_sum<LPG>(s, gmask);
-                const real w = rdiv_fast(yy[q], s);
-#pragma unroll
-                for (int v = 0; v < VPL; ++v)
-#pragma unroll
-                    for (int e = 0; e < EPV; ++e) sum[v].v[e] = fma(w, g[q][v].v[e], sum[v].v[e]);
-                if (FUSE) {
-#pragma unroll
-                    for (int v = 0; v < VPL; ++v) {
-                        if (!act[v]) continue;
-                        Pack<real> p;
-#pragma unroll
-                        for (int e = 0; e < EPV; ++e) p.v[e] = w * own[v].v[e];
-                        red_add_pack(acc_minor + (size_t)ccs[q] * ld + off[v], p);
-                    }
-                }
-            }
-        }
-        r = rn;
-        c = cn;
-        y = yn;
-    }
-    if (cur >= 0) {
-#pragma unroll
-        for (int v = 0; v < VPL; ++v)
-            if (act[v]) red_add_pack(acc + (size_t)cur * ld + off[v], sum[v]);
     }
 }
 
-// =============================================================================================
-// K2 (pipelined form) -- same contract as sweep_major_kernel without FUSE:
-//       acc[r, :] += sum_{n in segment} (Y[n] / dot(xown[r], xgat[c_n])) * xgat[c_n, :]
-// The probe of the bare access pattern (tools/gather_probe.cu, profiles/r01b_gather_probe_*.jsonl) moves
-// 48M random 208-byte rows out of a 48 MB L2 window in 0.58-0.60 ms, while the kernel above needs
-// 1.5 ms for the same gathers: every step serialises  shuffle -> gather -> dot -> butterfly -> divide ->
-// FMA, so a warp waits one full L2 round trip PLUS the dependent arithmetic per nnz, and lane-group
-// masked shuffles cost a MATCH/REDUX/VOTE/branch sequence each.  This form
-//   * keeps control flow uniform across the WARP (every group runs the same number of steps; steps past
-//     the end of a group's chunk are predicated off), so all shuffles use the full mask and compile to
-//     bare SHFL;
-//   * software-pipelines one step ahead: while step t is reduced and accumulated, the gathered row of
-//     step t+1 -- and, when the major id changes at t+1, the group's own row -- are already in flight.
-// =============================================================================================
-template <typename real, int LPG, int VPL, int MINB, int HINT>
-__global__ void __launch_bounds__(256, MINB)
-sweep_major_v2_kernel(const int* __restrict__ row, const int* __restrict__ col, const real* __restrict__ val,
-                      long long nnz, int chunk, const real* __restrict__ xown, const real* __restrict__ xgat,
-                      real* __restrict__ acc, int ld, int kw) {
-    constexpr int EPV = Pack<real>::N;
-    constexpr unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int gl = lane % LPG;
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    // warp-uniform exit: the first group of this warp already starts past the end
-    if (((tid - lane) / LPG) * (long long)chunk >= nnz) return;
-    const long long group = tid / LPG;
-    long long beg = group * (long long)chunk;
-    if (beg > nnz) beg = nnz;  // later groups of the last warp stay alive with an empty range
-    const long long end = (beg + chunk < nnz) ? beg + chunk : nnz;
-    const int nbatch = (chunk + LPG - 1) / LPG;  // identical for every group of the grid
+// shared memory of one warp: gather ring, own-row ring (DEPTH slots of VPL x 512 B each), two batches of
+// staged triples (32 x 16 B each)
+template <int VPL>
+struct SweepSmem {
+    static constexpr int DEPTH = 4;
+    static constexpr uint32_t SLOT = VPL * 512u;
+    static constexpr uint32_t RING = DEPTH * SLOT;
+    static constexpr uint32_t TRIP = 2u * 512u;
+    static constexpr uint32_t WARP = 2u * RING + TRIP;
+};
 
-    uint64_t pol_keep = 0, pol_stream = 0;
-    if (HINT) {
-        pol_keep = l2_policy_keep();
-        pol_stream = l2_policy_stream();
-    }
-    const unsigned row_bytes = (unsigned)ld * (unsigned)sizeof(real);
-    const char* gat_base = reinterpret_cast<const char*>(xgat);
-    const char* own_base = reinterpret_cast<const char*>(xown);
-    unsigned offb[VPL];  // byte offset of this lane's packs inside a row
-    bool act[VPL];
-#pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-        offb[v] = (unsigned)((gl + LPG * v) * EPV) * (unsigned)sizeof(real);
-        act[v] = (gl + LPG * v) * EPV < kw;
-    }
-
-    auto load_triple = [&](long long idx, int& r, int& c, real& y) {
-        r = -1;
-        c = 0;
-        y = real(0);
-        if (idx < end) {
-            if (HINT) {
-                r = ldg_stream(row + idx, pol_stream);
-                c = ldg_stream(col + idx, pol_stream);
-                y = ldg_stream(val + idx, pol_stream);
-            } else {
-                r = __ldg(row + idx);
-                c = __ldg(col + idx);
-                y = __ldg(val + idx);
-            }
-        }
-    };
-    auto gather = [&](int cc, bool valid, Pack<real>(&g)[VPL]) {
-        const char* src = gat_base + (uint64_t)(unsigned)cc * row_bytes;
-#pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-            if (valid && act[v]) {
-                if (HINT == 1)
-                    g[v] = ldg_pack_hint(reinterpret_cast<const real*>(src + offb[v]), pol_keep);
-                else
-                    g[v] = ldg_pack(reinterpret_cast<const real*>(src + offb[v]));
-            } else {
-                g[v] = pack_zero<real>();
-            }
-        }
-    };
-
-    Pack<real> own[VPL], own_nx[VPL], sum[VPL], g_nx[VPL];
-#pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-        own[v] = pack_zero<real>();
-        own_nx[v] = pack_zero<real>();
-        sum[v] = pack_zero<real>();
-    }
-    int cur = -1;
-
-    // batch 0 and the pipeline prologue (step 0 of batch 0)
-    int r, c;
-    real y;
-    load_triple(beg + gl, r, c, y);
-    int r_st = __shfl_sync(FULL, r, 0, LPG);
-    real y_st = __shfl_sync(FULL, y, 0, LPG);
-    {
-        const int c0 = __shfl_sync(FULL, c, 0, LPG);
-        gather(c0, r_st >= 0, g_nx);
-    }
-    bool chg_st = r_st >= 0;  // cur == -1: the first valid nnz always opens a row
-    if (chg_st) {
-        const char* src = own_base + (uint64_t)(unsigned)r_st * row_bytes;
-#pragma unroll
-        for (int v = 0; v < VPL; ++v)
-            if (act[v]) own_nx[v] = ldg_pack(reinterpret_cast<const real*>(src + offb[v]));
-    }
-
-    for (int b = 0; b < nbatch; ++b) {
-        int rn, cn;
-        real yn;
-        load_triple((b + 1 < nbatch) ? beg + (long long)(b + 1) * LPG + gl : end, rn, cn, yn);
-#pragma unroll
-        for (int t = 0; t < LPG; ++t) {
-            // ---- this step's operands were fetched one step ago
-            Pack<real> g[VPL];
-#pragma unroll
-            for (int v = 0; v < VPL; ++v) g[v] = g_nx[v];
-            const int rr = r_st;
-            const real yy = y_st;
-            const bool valid = rr >= 0;
-            if (chg_st) {  // divergent between groups, no shuffles inside
-                if (cur >= 0) {
-#pragma unroll
-                    for (int v = 0; v < VPL; ++v)
-                        if (act[v]) red_add_pack(acc + (size_t)cur * ld + (gl + LPG * v) * EPV, sum[v]);
-                }
-                cur = rr;
-#pragma unroll
-                for (int v = 0; v < VPL; ++v) {
-                    own[v] = own_nx[v];
-                    sum[v] = pack_zero<real>();
-                }
-            }
-            // ---- put the next step in flight (warp-uniform shuffles)
-            int c2, r2;
-            real y2;
-            if (t + 1 < LPG) {
-                c2 = __shfl_sync(FULL, c, t + 1, LPG);
-                r2 = __shfl_sync(FULL, r, t + 1, LPG);
-                y2 = __shfl_sync(FULL, y, t + 1, LPG);
-            } else {
-                c2 = __shfl_sync(FULL, cn, 0, LPG);
-                r2 = __shfl_sync(FULL, rn, 0, LPG);
-                y2 = __shfl_sync(FULL, yn, 0, LPG);
-            }
-            gather(c2, r2 >= 0, g_nx);
-            chg_st = r2 >= 0 && r2 != cur;
-            if (chg_st) {
-                const char* src = own_base + (uint64_t)(unsigned)r2 * row_bytes;
-#pragma unroll
-                for (int v = 0; v < VPL; ++v)
-                    if (act[v]) own_nx[v] = ldg_pack(reinterpret_cast<const real*>(src + offb[v]));
-            }
-            r_st = r2;
-            y_st = y2;
-            // ---- reduce and accumulate the current step (pad / invalid lanes carry zeros)
-            real s0 = real(0), s1 = real(0);
-#pragma unroll
-            for (int v = 0; v < VPL; ++v) {
-                s0 = fma(own[v].v[0], g[v].v[0], s0);
-                s1 = fma(own[v].v[1], g[v].v[1], s1);
-                if (EPV == 4) {
-                    s0 = fma(own[v].v[EPV - 2], g[v].v[EPV - 2], s0);
-                    s1 = fma(own[v].v[EPV - 1], g[v].v[EPV - 1], s1);
-                }
-            }
-            real s = s0 + s1;
-#pragma unroll
-            for (int o = LPG / 2; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o, LPG);
-            const real w = valid ? rdiv_fast(yy, s) : real(0);
-#pragma unroll
-            for (int v = 0; v < VPL; ++v)
-#pragma unroll
-                for (int e = 0; e < EPV; ++e) sum[v].v[e] = fma(w, g[v].v[e], sum[v].v[e]);
-        }
-        r = rn;
-        c = cn;
-        y = yn;
-    }
-    if (cur >= 0) {
-#pragma unroll
-        for (int v = 0; v < VPL; ++v)
-            if (act[v]) red_add_pack(acc + (size_t)cur * ld + (gl + LPG * v) * EPV, sum[v]);
-    }
+// staged triple, 16 bytes: float {row, col, y, row}; double {row, col, y}
+__device__ __forceinline__ void sts_triple(uint32_t addr, int r, int c, float y) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r), "r"(c), "r"(__float_as_int(y)), "r"(r) : "memory");
+}
+__device__ __forceinline__ void sts_triple(uint32_t addr, int r, int c, double y) {
+    const long long yb = __double_as_longlong(y);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r), "r"(c), "r"((int)(yb & 0xffffffffll)),
+                 "r"((int)(yb >> 32))
+                 : "memory");
+}
+__device__ __forceinline__ void lds_row_y(uint32_t addr, int& r, float& y) {
+    int yb;
+    lds64(addr + 8u, yb, r);
+    y = __int_as_float(yb);
+}
+__device__ __forceinline__ void lds_row_y(uint32_t addr, int& r, double& y) {
+    int c, lo, hi;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r), "=r"(c), "=r"(lo), "=r"(hi) : "r"(addr));
+    y = __longlong_as_double(((long long)hi << 32) | (unsigned)lo);
 }
 
 // =============================================================================================
-// K2 (deep-pipeline form) -- same contract again:
-//       acc[r, :] += sum_{n in segment} (Y[n] / dot(xown[r], xgat[c_n])) * xgat[c_n, :]
-// Measured (profiles/r01b_tune_v2.jsonl): the one-step register pipeline above still needs 1.45 ms per
-// pass where the bare gathers take 0.6 ms.  A warp advances one step per memory round trip, the round
-// trip is the MAXIMUM over its lane groups' loads (gathers that miss L2, own rows and triples streamed
-// from DRAM), and registers cap how many rows a warp can keep in flight.  Here the rows land in SHARED
-// memory instead: every lane copies its own 16-byte packs with cp.async (LDGSTS, per-thread, no
-// per-copy descriptor like the bulk/TMA path of hpf_sweep_tma.cuh) DEPTH-1 steps ahead of their use and
-// reads back exactly the packs it copied, so no barrier or cross-lane hand-off is needed.  The own row
-// of an upcoming major-id change is staged the same way in a second ring; triples are fetched two
-// batches ahead.  Control flow is warp-uniform (full-mask shuffles).
-//   shared memory per warp: 2 rings x DEPTH slots x VPL x 512 B.
+// ngroups: number of lane groups of the launch = padded nnz / chunk, a multiple of 32 / LPG.
+// chunk:   nnz per lane group, a multiple of LPG.  row/col/val hold ngroups * chunk entries.
 // =============================================================================================
-template <typename real, int LPG, int VPL, int MINB, int HINT, int BLOCK>
+template <typename real, int LPG, int VPL, int MINB, int BLOCK, int HINT, bool FULLROW, bool ROBUST>
 __global__ void __launch_bounds__(BLOCK, MINB)
-sweep_major_v3_kernel(const int* __restrict__ row, const int* __restrict__ col, const real* __restrict__ val,
-                      long long nnz, int chunk, const real* __restrict__ xown, const real* __restrict__ xgat,
-                      real* __restrict__ acc, int ld, int kw) {
+sweep_rows_kernel(const int* __restrict__ row, const int* __restrict__ col, const real* __restrict__ val,
+                  long long ngroups, int chunk, const real* __restrict__ xown, const real* __restrict__ xgat,
+                  real* __restrict__ acc, int ld, int kw, RescueArgs<real> rescue) {
     constexpr int EPV = Pack<real>::N;
-    constexpr int DEPTH = 4;  // ring slots; LPG is a multiple of 4, so the slot of step t is t % 4 at compile time
-    constexpr int LOOK = DEPTH - 1;
+    constexpr int NG = 32 / LPG;  // lane groups per warp
+    using SM = SweepSmem<VPL>;
+    constexpr int DEPTH = SM::DEPTH, LOOK = DEPTH - 1;
     static_assert(LPG % DEPTH == 0, "lane-group width must be a multiple of the ring depth");
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr uint32_t SLOT_BYTES = VPL * 32 * 16;            // one step of one warp: [v][lane] packs
-    constexpr uint32_t WARP_BYTES = 2 * DEPTH * SLOT_BYTES;   // gather ring, then own-row ring
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gl = lane % LPG;
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (((tid - lane) / LPG) * (long long)chunk >= nnz) return;  // warp-uniform
-    const long long group = tid / LPG;
-    long long beg = group * (long long)chunk;
-    if (beg > nnz) beg = nnz;
-    const long long end = (beg + chunk < nnz) ? beg + chunk : nnz;
-    const int nbatch = (chunk + LPG - 1) / LPG;
+    const int gl = lane % LPG, g = lane / LPG;
+    const long long wg0 = ((long long)blockIdx.x * (BLOCK / 32) + warp) * NG;
+    if (wg0 >= ngroups) return;  // warp-uniform
+    const long long beg = (wg0 + g) * (long long)chunk;
+    const int nbatch = chunk / LPG;
 
-    uint64_t pol_stream = 0;
-    if (HINT) pol_stream = l2_policy_stream();
+    uint64_t pol_keep = 0, pol_stream = 0;
+    if (HINT) {
+        pol_keep = l2_policy_keep();
+        pol_stream = l2_policy_stream();
+    }
     const unsigned row_bytes = (unsigned)ld * (unsigned)sizeof(real);
-    const uint32_t ring_g = smem_u32(smem_raw) + (uint32_t)warp * WARP_BYTES + (uint32_t)lane * 16u;
-    const uint32_t ring_o = ring_g + DEPTH * SLOT_BYTES;
-    // every lane reads back exactly the cells it copies; cells of packs beyond the row's active width
-    // are never copied, so zeroing them once makes every later read a plain LDS (no per-step predication)
-#pragma unroll
-    for (int q = 0; q < 2 * DEPTH * VPL; ++q) sts_pack<real>(ring_g + (uint32_t)q * 512u, pack_zero<real>());
-    const unsigned off0 = (unsigned)(gl * EPV) * (unsigned)sizeof(real);  // byte offset of this lane's first pack
-    const char* gat_lane = reinterpret_cast<const char*>(xgat) + off0;
-    const char* own_lane = reinterpret_cast<const char*>(xown) + off0;
-    bool act[VPL];
-#pragma unroll
-    for (int v = 0; v < VPL; ++v) act[v] = (gl + LPG * v) * EPV < kw;
-
-    auto load_triple = [&](long long idx, int& r, int& c, real& y) {
-        r = -1;
-        c = 0;
-        y = real(0);
-        if (idx < end) {
-            if (HINT) {
-                r = ldg_stream(row + idx, pol_stream);
-                c = ldg_stream(col + idx, pol_stream);
-                y = ldg_stream(val + idx, pol_stream);
-            } else {
-                r = __ldg(row + idx);
-                c = __ldg(col + idx);
-                y = __ldg(val + idx);
-            }
-        }
-    };
-    // stage one step: the gathered row always, the own row when the major id changes at that step
-    auto stage = [&](int slot, int ra, int ca, int r_before) {
-        if (ra >= 0) {
-            const char* src = gat_lane + (uint64_t)(unsigned)ca * row_bytes;
-#pragma unroll
-            for (int v = 0; v < VPL; ++v)
-                if (act[v])
-                    cp_async16(ring_g + (uint32_t)slot * SLOT_BYTES + (uint32_t)v * 512u, src + v * (LPG * 16));
-            if (ra != r_before) {
-                const char* so = own_lane + (uint64_t)(unsigned)ra * row_bytes;
-#pragma unroll
-                for (int v = 0; v < VPL; ++v)
-                    if (act[v])
-                        cp_async16(ring_o + (uint32_t)slot * SLOT_BYTES + (uint32_t)v * 512u, so + v * (LPG * 16));
-            }
-        }
-        cp_async_commit();
-    };
-
-    Pack<real> own[VPL], sum[VPL];
-#pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-        own[v] = pack_zero<real>();
-        sum[v] = pack_zero<real>();
-    }
-    int cur = -1;
-
-    // triples: batch b in (r0,c0,y0), b+1 in (r1,c1,y1), b+2 loaded at the top of batch b
-    int r0, c0, r1, c1, r2 = -1, c2 = 0;
-    real y0, y1, y2 = real(0);
-    load_triple(beg + gl, r0, c0, y0);
-    load_triple((1 < nbatch) ? beg + LPG + gl : end, r1, c1, y1);
-    // prologue: stage steps 0 .. DEPTH-2 (inside batch 0 since DEPTH-2 < LPG); rq[] = major ids of the
-    // staged-but-not-consumed steps, oldest first
-    int r_staged = -1;  // major id of the most recently staged valid step
-    int rq[LOOK];
-#pragma unroll
-    for (int t = 0; t < LOOK; ++t) {
-        const int ra = __shfl_sync(FULL, r0, t, LPG);
-        const int ca = __shfl_sync(FULL, c0, t, LPG);
-        stage(t, ra, ca, r_staged);
-        if (ra >= 0) r_staged = ra;
-        rq[t] = ra;
-    }
-
-    for (int b = 0; b < nbatch; ++b) {
-        load_triple((b + 2 < nbatch) ? beg + (long long)(b + 2) * LPG + gl : end, r2, c2, y2);
-#pragma unroll
-        for (int t = 0; t < LPG; ++t) {
-            // ---- stage step t + LOOK (this batch or the next one)
-            int ra, ca;
-            if (t + LOOK < LPG) {
-                ra = __shfl_sync(FULL, r0, t + LOOK, LPG);
-                ca = __shfl_sync(FULL, c0, t + LOOK, LPG);
-            } else {
-                ra = __shfl_sync(FULL, r1, t + LOOK - LPG, LPG);
-                ca = __shfl_sync(FULL, c1, t + LOOK - LPG, LPG);
-            }
-            stage((t + LOOK) % DEPTH, ra, ca, r_staged);
-            if (ra >= 0) r_staged = ra;
-            cp_async_wait<LOOK>();  // everything but the newest LOOK groups has landed: step t is in
-            // ---- consume step t
-            const int rr = rq[0];
-#pragma unroll
-            for (int q = 0; q + 1 < LOOK; ++q) rq[q] = rq[q + 1];
-            rq[LOOK - 1] = ra;
-            const real yy = __shfl_sync(FULL, y0, t, LPG);
-            const bool valid = rr >= 0;
-            const uint32_t slot_off = (uint32_t)(t % DEPTH) * SLOT_BYTES;
-            if (valid && rr != cur) {  // divergent between groups, no shuffles inside
-                if (cur >= 0) {
-#pragma unroll
-                    for (int v = 0; v < VPL; ++v)
-                        if (act[v]) red_add_pack(acc + (size_t)cur * ld + (gl + LPG * v) * EPV, sum[v]);
-                }
-                cur = rr;
-#pragma unroll
-                for (int v = 0; v < VPL; ++v) {
-                    own[v] = lds_pack<real>(ring_o + slot_off + (uint32_t)v * 512u);
-                    sum[v] = pack_zero<real>();
-                }
-            }
-            Pack<real> g[VPL];
-#pragma unroll
-            for (int v = 0; v < VPL; ++v) g[v] = lds_pack<real>(ring_g + slot_off + (uint32_t)v * 512u);
-            real s0 = real(0), s1 = real(0);
-#pragma unroll
-            for (int v = 0; v < VPL; ++v) {
-                s0 = fma(own[v].v[0], g[v].v[0], s0);
-                s1 = fma(own[v].v[1], g[v].v[1], s1);
-                if (EPV == 4) {
-                    s0 = fma(own[v].v[EPV - 2], g[v].v[EPV - 2], s0);
-                    s1 = fma(own[v].v[EPV - 1], g[v].v[EPV - 1], s1);
-                }
-            }
-            real s = s0 + s1;
-#pragma unroll
-            for (int o = LPG / 2; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o, LPG);
-            // steps past the end of the chunk read a stale (finite) slot: their weight is forced to zero
-            const real w = valid ? rdiv_rcp(yy, s) : real(0);
-#pragma unroll
-            for (int v = 0; v < VPL; ++v)
-#pragma unroll
-                for (int e = 0; e < EPV; ++e) sum[v].v[e] = fma(w, g[v].v[e], sum[v].v[e]);
-        }
-        r0 = r1; c0 = c1; y0 = y1;
-        r1 = r2; c1 = c2; y1 = y2;
-    }
-    cp_async_wait<0>();
-    if (cur >= 0) {
-#pragma unroll
-        for (int v = 0; v < VPL; ++v)
-            if (act[v]) red_add_pack(acc + (size_t)cur * ld + (gl + LPG * v) * EPV, sum[v]);
-    }
-}
-
-// =============================================================================================
-// K2 (deep pipeline, shuffle-free triples).  ncu on the form above (profiles/r01b_ncu_full_v3_pipeline.csv):
-// memory latency is hidden (long-scoreboard stalls 0.2 per issue) and the kernel is bound by the LSU pipe
-// (59 %) / issue (66 %); of the ~10 LSU instructions per step, six are shuffles -- three of them only
-// broadcast the step's (major id, minor id, count) from the lane that loaded it.  Here every lane
-// reads the triples of FOUR consecutive steps itself with one 128-bit load per array (all lanes of a
-// group read the same address, one sector), so the only shuffles left are the butterfly of the
-// normaliser.  Batches are 4 steps (= the ring depth) for every lane-group width; needs chunk % 4 == 0
-// and triple arrays padded by 4 entries (the host falls back to the form above otherwise).
-// =============================================================================================
-template <typename real, int LPG, int VPL, int MINB, int HINT, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, MINB)
-sweep_major_v4_kernel(const int* __restrict__ row, const int* __restrict__ col, const real* __restrict__ val,
-                      long long nnz, int chunk, const real* __restrict__ xown, const real* __restrict__ xgat,
-                      real* __restrict__ acc, int ld, int kw) {
-    constexpr int EPV = Pack<real>::N;
-    constexpr int DEPTH = 4, LOOK = DEPTH - 1, B4 = 4;
-    constexpr unsigned FULL = 0xffffffffu;
-    constexpr uint32_t SLOT_BYTES = VPL * 32 * 16;
-    constexpr uint32_t WARP_BYTES = 2 * DEPTH * SLOT_BYTES;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gl = lane % LPG;
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (((tid - lane) / LPG) * (long long)chunk >= nnz) return;  // warp-uniform
-    const long long group = tid / LPG;
-    long long beg = group * (long long)chunk;
-    if (beg > nnz) beg = nnz;
-    const long long end = (beg + chunk < nnz) ? beg + chunk : nnz;
-    const int nbatch = (chunk + B4 - 1) / B4;
-
-    const unsigned row_bytes = (unsigned)ld * (unsigned)sizeof(real);
-    const uint32_t ring_g = smem_u32(smem_raw) + (uint32_t)warp * WARP_BYTES + (uint32_t)lane * 16u;
-    const uint32_t ring_o = ring_g + DEPTH * SLOT_BYTES;
-#pragma unroll
-    for (int q = 0; q < 2 * DEPTH * VPL; ++q) sts_pack<real>(ring_g + (uint32_t)q * 512u, pack_zero<real>());
+    const uint32_t wbase = smem_u32(smem_raw) + (uint32_t)warp * SM::WARP;
+    const uint32_t ring_g = wbase + (uint32_t)lane * 16u;
+    const uint32_t ring_o = ring_g + SM::RING;
+    const uint32_t trip0 = wbase + 2u * SM::RING + (uint32_t)g * 16u;  // + buffer*512 + t*NG*16
     const unsigned off0 = (unsigned)(gl * EPV) * (unsigned)sizeof(real);
     const char* gat_lane = reinterpret_cast<const char*>(xgat) + off0;
     const char* own_lane = reinterpret_cast<const char*>(xown) + off0;
+    // src-size of each pack's copy: 16, or 0 (zero-fill) beyond the active width
+    uint32_t sz[VPL];
     bool act[VPL];
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) act[v] = (gl + LPG * v) * EPV < kw;
+    for (int v = 0; v < VPL; ++v) {
+        act[v] = (gl + LPG * v) * EPV < kw;
+        sz[v] = (FULLROW || act[v]) ? 16u : 0u;
+    }
 
-    // one batch = 4 consecutive triples, identical in every lane of the group; entries past the end of
-    // the chunk get major id -1
-    auto load_batch = [&](long long idx, int (&r)[4], int (&c)[4], real (&y)[4]) {
-        if (idx < end) {
-            ldg4(row + idx, r);
-            ldg4(col + idx, c);
-            ldg4(val + idx, y);
-#pragma unroll
-            for (int j = 1; j < 4; ++j)
-                if (idx + j >= end) r[j] = -1;
+    auto load_triple = [&](int b, int& r, int& c, real& y) {
+        const long long idx = beg + (long long)b * LPG + gl;
+        if (HINT) {
+            r = ldg_stream(row + idx, pol_stream);
+            c = ldg_stream(col + idx, pol_stream);
+            y = ldg_stream(val + idx, pol_stream);
         } else {
+            r = __ldg(row + idx);
+            c = __ldg(col + idx);
+            y = __ldg(val + idx);
+        }
+    };
+    auto copy_row = [&](uint32_t dst, const char* src, uint64_t pol) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                r[j] = -1;
-                c[j] = 0;
-                y[j] = real(0);
+        for (int v = 0; v < VPL; ++v) {
+            if (FULLROW) {
+                if (HINT) cp_async16_pol(dst + (uint32_t)v * 512u, src + v * (LPG * 16), pol);
+                else cp_async16(dst + (uint32_t)v * 512u, src + v * (LPG * 16));
+            } else {
+                if (HINT) cp_async16_sz_pol(dst + (uint32_t)v * 512u, src + v * (LPG * 16), sz[v], pol);
+                else cp_async16_sz(dst + (uint32_t)v * 512u, src + v * (LPG * 16), sz[v]);
             }
         }
     };
-    auto stage = [&](int slot, int ra, int ca, int r_before) {
-        if (ra >= 0) {
-            const char* src = gat_lane + (uint64_t)(unsigned)ca * row_bytes;
-#pragma unroll
-            for (int v = 0; v < VPL; ++v)
-                if (act[v])
-                    cp_async16(ring_g + (uint32_t)slot * SLOT_BYTES + (uint32_t)v * 512u, src + v * (LPG * 16));
-            if (ra != r_before) {
-                const char* so = own_lane + (uint64_t)(unsigned)ra * row_bytes;
-#pragma unroll
-                for (int v = 0; v < VPL; ++v)
-                    if (act[v])
-                        cp_async16(ring_o + (uint32_t)slot * SLOT_BYTES + (uint32_t)v * 512u, so + v * (LPG * 16));
-            }
+    int r_staged = -1;
+    // stage one step: the gathered row always, the own row when the row id changes at that step
+    auto stage = [&](int slot, uint32_t trip_addr) {
+        int ra, ca;
+        lds64(trip_addr, ra, ca);
+        copy_row(ring_g + (uint32_t)slot * SM::SLOT, gat_lane + (uint64_t)(unsigned)ca * row_bytes, pol_keep);
+        if (ra != r_staged) {
+            copy_row(ring_o + (uint32_t)slot * SM::SLOT, own_lane + (uint64_t)(unsigned)ra * row_bytes, pol_stream);
+            r_staged = ra;
         }
         cp_async_commit();
     };
@@ -617,42 +278,48 @@ sweep_major_v4_kernel(const int* __restrict__ row, const int* __restrict__ col, 
         sum[v] = pack_zero<real>();
     }
     int cur = -1;
-
-    int rA[4], cA[4], rB[4], cB[4], rC[4], cC[4];
-    real yA[4], yB[4], yC[4];
-    load_batch(beg, rA, cA, yA);
-    load_batch(beg + B4, rB, cB, yB);
-    int r_staged = -1;
-    int rq[LOOK];
+    auto flush = [&]() {
 #pragma unroll
-    for (int t = 0; t < LOOK; ++t) {
-        stage(t, rA[t], cA[t], r_staged);
-        if (rA[t] >= 0) r_staged = rA[t];
-        rq[t] = rA[t];
+        for (int v = 0; v < VPL; ++v)
+            if (act[v]) {
+                real* dst = acc + (size_t)cur * ld + (gl + LPG * v) * EPV;
+                if (HINT) red_add_pack_pol(dst, sum[v], pol_stream);
+                else red_add_pack(dst, sum[v]);
+            }
+    };
+
+    // ---- prologue: batches 0 and 1 into the two triple buffers, first LOOK steps staged ------------
+    {
+        int r, c;
+        real y;
+        load_triple(0, r, c, y);
+        sts_triple(trip0 + (uint32_t)gl * (NG * 16u), r, c, y);
+        load_triple(nbatch > 1 ? 1 : 0, r, c, y);
+        sts_triple(trip0 + 512u + (uint32_t)gl * (NG * 16u), r, c, y);
     }
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < LOOK; ++t) stage(t, trip0 + (uint32_t)t * (NG * 16u));
 
+    uint32_t tb_cur = trip0, tb_nxt = trip0 + 512u;
     for (int b = 0; b < nbatch; ++b) {
-        load_batch(beg + (long long)(b + 2) * B4, rC, cC, yC);
+        // triples of batch b+2 (clamped: the tail re-reads the last batch, whose staging is never consumed)
+        int r2, c2;
+        real y2;
+        load_triple(b + 2 < nbatch ? b + 2 : nbatch - 1, r2, c2, y2);
 #pragma unroll
-        for (int t = 0; t < B4; ++t) {
-            const int ra = (t + LOOK < B4) ? rA[(t + LOOK) % B4] : rB[(t + LOOK) % B4];
-            const int ca = (t + LOOK < B4) ? cA[(t + LOOK) % B4] : cB[(t + LOOK) % B4];
-            stage((t + LOOK) % DEPTH, ra, ca, r_staged);
-            if (ra >= 0) r_staged = ra;
-            cp_async_wait<LOOK>();
-            const int rr = rq[0];
-#pragma unroll
-            for (int q = 0; q + 1 < LOOK; ++q) rq[q] = rq[q + 1];
-            rq[LOOK - 1] = ra;
-            const real yy = yA[t];
-            const bool valid = rr >= 0;
-            const uint32_t slot_off = (uint32_t)(t % DEPTH) * SLOT_BYTES;
-            if (valid && rr != cur) {
-                if (cur >= 0) {
-#pragma unroll
-                    for (int v = 0; v < VPL; ++v)
-                        if (act[v]) red_add_pack(acc + (size_t)cur * ld + (gl + LPG * v) * EPV, sum[v]);
-                }
+        for (int t = 0; t < LPG; ++t) {
+            // ---- stage step t + LOOK (this batch or the next one)
+            if (t + LOOK < LPG) stage((t + LOOK) % DEPTH, tb_cur + (uint32_t)(t + LOOK) * (NG * 16u));
+            else stage((t + LOOK) % DEPTH, tb_nxt + (uint32_t)(t + LOOK - LPG) * (NG * 16u));
+            cp_async_wait<LOOK>();  // all but the newest LOOK groups have landed: step t is in
+            // ---- consume step t
+            int rr;
+            real yy;
+            lds_row_y(tb_cur + (uint32_t)t * (NG * 16u), rr, yy);
+            const uint32_t slot_off = (uint32_t)(t % DEPTH) * SM::SLOT;
+            if (rr != cur) {  // divergent between groups, no shuffles inside
+                if (cur >= 0) flush();
                 cur = rr;
 #pragma unroll
                 for (int v = 0; v < VPL; ++v) {
@@ -660,53 +327,56 @@ sweep_major_v4_kernel(const int* __restrict__ row, const int* __restrict__ col, 
                     sum[v] = pack_zero<real>();
                 }
             }
-            Pack<real> g[VPL];
+            Pack<real> gv[VPL];
 #pragma unroll
-            for (int v = 0; v < VPL; ++v) g[v] = lds_pack<real>(ring_g + slot_off + (uint32_t)v * 512u);
-            real s0 = real(0), s1 = real(0);
+            for (int v = 0; v < VPL; ++v) gv[v] = lds_pack<real>(ring_g + slot_off + (uint32_t)v * 512u);
+            typename DotOf<real>::type d0, d1;
 #pragma unroll
             for (int v = 0; v < VPL; ++v) {
-                s0 = fma(own[v].v[0], g[v].v[0], s0);
-                s1 = fma(own[v].v[1], g[v].v[1], s1);
-                if (EPV == 4) {
-                    s0 = fma(own[v].v[EPV - 2], g[v].v[EPV - 2], s0);
-                    s1 = fma(own[v].v[EPV - 1], g[v].v[EPV - 1], s1);
-                }
+                if (v & 1) d1.add(own[v], gv[v]);
+                else d0.add(own[v], gv[v]);
             }
-            real s = s0 + s1;
+            real s = VPL > 1 ? d0.total() + d1.total() : d0.total();
 #pragma unroll
             for (int o = LPG / 2; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o, LPG);
-            const real w = valid ? rdiv_rcp(yy, s) : real(0);
+            real w = rdiv_rcp(yy, s);
+            if (ROBUST) {
+                if (!(s >= rescue_threshold<real>())) {  // group-uniform (s is the group's sum)
+                    if (yy > real(0)) {
+                        int ra_, ca_;
+                        lds64(tb_cur + (uint32_t)t * (NG * 16u), ra_, ca_);
+                        sweep_rescue<real, LPG, VPL>(rescue, cur, ca_, yy, ld, gl);
+                    }
+                    w = real(0);
+                }
+            }
 #pragma unroll
-            for (int v = 0; v < VPL; ++v)
-#pragma unroll
-                for (int e = 0; e < EPV; ++e) sum[v].v[e] = fma(w, g[v].v[e], sum[v].v[e]);
+            for (int v = 0; v < VPL; ++v) axpy_pack(sum[v], w, gv[v]);
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            rA[j] = rB[j]; cA[j] = cB[j]; yA[j] = yB[j];
-            rB[j] = rC[j]; cB[j] = cC[j]; yB[j] = yC[j];
-        }
+        // batch b is consumed: its buffer takes batch b+2
+        __syncwarp();
+        sts_triple(tb_cur + (uint32_t)gl * (NG * 16u), r2, c2, y2);
+        __syncwarp();
+        const uint32_t tmp = tb_cur;
+        tb_cur = tb_nxt;
+        tb_nxt = tmp;
     }
     cp_async_wait<0>();
-    if (cur >= 0) {
-#pragma unroll
-        for (int v = 0; v < VPL; ++v)
-            if (act[v]) red_add_pack(acc + (size_t)cur * ld + (gl + LPG * v) * EPV, sum[v]);
-    }
+    if (cur >= 0) flush();
 }
 
 // =============================================================================================
 // K2'  single-pass COO sweep with atomics on both sides: any nnz order, used for minibatches
 //      (partial_fit pxi:438-459, SVI pxi:292-314) and as the cross-check of the two-pass sweep.
 //      accU[u,:] += w_n * xi[i,:]    accI[i,:] += w_n * xu[u,:]     (optionally phi[n,:] written)
+//      ROBUST: normalisers below rescue_threshold take the reference's own per-nnz softmax (sweep_rescue).
 // =============================================================================================
-template <typename real, int LPG, int VPL>
+template <typename real, int LPG, int VPL, bool ROBUST>
 __global__ void __launch_bounds__(256)
 sweep_coo_kernel(const int* __restrict__ iu, const int* __restrict__ ii, const real* __restrict__ val,
                  long long nnz, int chunk, const real* __restrict__ xu, const real* __restrict__ xi,
                  real* __restrict__ accU, real* __restrict__ accI, int ld,
-                 real* __restrict__ phi, int k) {
+                 real* __restrict__ phi, int k, RescueArgs<real> rescue) {
     constexpr int EPV = Pack<real>::N;
     const int gl = (threadIdx.x & 31) % LPG;
     const long long group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPG;
@@ -747,7 +417,15 @@ sweep_coo_kernel(const int* __restrict__ iu, const int* __restrict__ ii, const r
 #pragma unroll
                 for (int e = 0; e < EPV; ++e) s = fma(gu[v].v[e], gi[v].v[e], s);
             s = group_sum<LPG>(s, gmask);
-            const real w = rdiv_fast(yy, s);
+            real w = rdiv_fast(yy, s);
+            bool rescued = false;
+            if (ROBUST) {
+                if (!(s >= rescue_threshold<real>())) {  // group-uniform
+                    sweep_rescue<real, LPG, VPL>(rescue, uu, it, yy, ld, gl, phi ? phi + (size_t)(base + t) * k : nullptr);
+                    w = real(0);
+                    rescued = true;
+                }
+            }
 #pragma unroll
             for (int v = 0; v < VPL; ++v) {
                 if (!act[v]) continue;
@@ -759,7 +437,7 @@ sweep_coo_kernel(const int* __restrict__ iu, const int* __restrict__ ii, const r
                 }
                 red_add_pack(accU + (size_t)uu * ld + off[v], pu);
                 red_add_pack(accI + (size_t)it * ld + off[v], pi);
-                if (phi != nullptr) {
+                if (phi != nullptr && !rescued) {
 #pragma unroll
                     for (int e = 0; e < EPV; ++e)
                         if (off[v] + e < k)

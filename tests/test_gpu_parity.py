@@ -74,7 +74,7 @@ def test_full_batch_fp64_odd_shapes(golden_odd):
     hyp = dict(a=0.5, a_prime=0.4, b_prime=1.3, c=0.6, c_prime=0.2, d_prime=0.8)
     for its, tol in ((1, 1e-12), (25, 1e-10)):
         out = _fit_gpu(g["Y"], g["ix_u"], g["ix_i"], int(g["nU"]), int(g["nI"]), int(g["k"]), its, 5, hyp=hyp,
-                       chunk=5)
+                       chunk=32)
         for key in STATE_KEYS:
             assert relerr(out[key], g["it%d_%s" % (its, key)]) < tol, key
 
@@ -109,7 +109,7 @@ def test_sweep_all_row_shapes_vs_oracle(k, dtype):
         O.cavi_full_iteration(ref, y, u, i, **HYP)
     tol = 1e-11 if dtype == np.float64 else 2e-5
     for sweep in (0, 1):
-        out = _fit_gpu(y, u, i, nU, nI, k, 2, 11, dtype=dtype, sweep=sweep, panel_mb=0.05, chunk=48)
+        out = _fit_gpu(y, u, i, nU, nI, k, 2, 11, dtype=dtype, sweep=sweep, panel_mb=0.05, chunk=64)
         for key in STATE_KEYS:
             assert relerr(out[key], ref[key]) < tol, (key, sweep)
 
@@ -214,7 +214,7 @@ def test_edge_cases():
     i = np.arange(2000, dtype=np.int32)
     y = np.ones(2000)
     st = O.initialize_parameters(nU, nI, k, 2, 0.3, 1.0, 0.3, 1.0)
-    eng = _engine_from(st, k, np.float64, chunk=16)
+    eng = _engine_from(st, k, np.float64, chunk=32)
     eng.load_coo(u, i, y)
     eng.step_full(3)
     out = eng.export_all()
@@ -323,21 +323,29 @@ def test_wide_rows_vs_oracle(k, dtype):
         assert relerr(out[key], ref[key]) < tol, key
 
 
-@pytest.mark.parametrize("sweep", [2, 3, 4])
+# every compiled shape of sweep_rows_kernel per row class: (lanes per row, CTA size)
+SHAPES = {10: [(0, 0)], 30: [(4, 256), (4, 128), (8, 256)], 50: [(4, 128), (8, 256), (8, 128), (4, 64)],
+          128: [(8, 128), (16, 256), (16, 128), (8, 64)]}
+
+
 @pytest.mark.parametrize("k,dtype", [(10, np.float64), (50, np.float32), (30, np.float32), (128, np.float32)])
-def test_alternative_sweeps_vs_oracle(golden_full, sweep, k, dtype):
-    """The one-pass (gather + RED) sweeps (2: user-major walk, 4: item-major walk) and the
-    cp.async.bulk/mbarrier staged-gather sweep (3) compute the same iteration as the default two-pass
-    register-gather sweep."""
+def test_sweep_shapes_vs_oracle(golden_full, k, dtype):
+    """Every compiled lane-group shape of the sweep kernel, with and without L2 policies, with whole-stride
+    copies (fullrow) where the row class has them, computes the same iterations as the oracle."""
     g = golden_full
     st0 = O.initialize_parameters(100, 100, k, 123, 0.3, 1.0, 0.3, 1.0, dtype)
     ref = {k_: v.astype(np.float64) for k_, v in st0.items()}
     for _ in range(3):
         O.cavi_full_iteration(ref, g["Y"], g["ix_u"], g["ix_i"], **HYP)
-    out = _fit_gpu(g["Y"], g["ix_u"], g["ix_i"], 100, 100, k, 3, 123, dtype=dtype, sweep=sweep, chunk=40)
     tol = 1e-11 if dtype == np.float64 else 3e-5
-    for key in STATE_KEYS:
-        assert relerr(out[key], ref[key]) < tol, (key, sweep)
+    for lpg, block in SHAPES[k]:
+        for hint, fullrow in ((1, 0), (0, 0), (1, 1), (0, 1)):
+            if k != 50 and (hint, fullrow) != (1, 0):
+                continue   # the measurement variants are only built for the headline row class
+            out = _fit_gpu(g["Y"], g["ix_u"], g["ix_i"], 100, 100, k, 3, 123, dtype=dtype, lpg=lpg, block=block, hint=hint,
+                           fullrow=fullrow, strict=1, chunk=64, panel_mb=0.004)
+            for key in STATE_KEYS:
+                assert relerr(out[key], ref[key]) < tol, (key, lpg, block, hint, fullrow)
 
 
 def test_step_batch_ids_equals_explicit_batch(golden_full):
@@ -430,11 +438,11 @@ def test_row_alignment_is_result_neutral(monkeypatch, golden_full, align, k, dty
     for _ in range(3):
         O.cavi_full_iteration(ref, g["Y"], g["ix_u"], g["ix_i"], **HYP)
     tol = 1e-11 if dtype == np.float64 else 3e-5
-    for sweep, kernel in ((0, 1), (0, 2), (0, 3), (0, 4), (1, 1), (2, 1), (4, 1)):
-        out = _fit_gpu(g["Y"], g["ix_u"], g["ix_i"], 100, 100, k, 3, 123, dtype=dtype, sweep=sweep, kernel=kernel,
-                       chunk=24, panel_mb=0.004)
+    for sweep in (0, 1):
+        out = _fit_gpu(g["Y"], g["ix_u"], g["ix_i"], 100, 100, k, 3, 123, dtype=dtype, sweep=sweep, chunk=32,
+                       panel_mb=0.004)
         for key in STATE_KEYS:
-            assert relerr(out[key], ref[key]) < tol, (key, sweep, kernel, align)
+            assert relerr(out[key], ref[key]) < tol, (key, sweep, align)
 
 
 def test_row_alignment_minibatch_and_metrics(monkeypatch, golden_full, golden_pf):
@@ -450,7 +458,7 @@ def test_engine_options_from_environment(monkeypatch, golden_full):
     from hpfrec_b200 import _lib
     from hpfrec_b200.engine import Engine
     g = golden_full
-    monkeypatch.setenv("HPF_OPTIONS", "sweep=4,chunk=32,panel_mb=0.01")
+    monkeypatch.setenv("HPF_OPTIONS", "sweep=1,chunk=32,panel_mb=0.01")
     out = _fit_gpu(g["Y"], g["ix_u"], g["ix_i"], 100, 100, 10, 10, 123)
     for key in STATE_KEYS:
         assert relerr(out[key], g["it10_%s" % key]) < 1e-11, key
@@ -465,13 +473,10 @@ def test_engine_options_from_environment(monkeypatch, golden_full):
 @pytest.mark.parametrize("k,dtype", [(4, np.float32), (7, np.float64), (10, np.float64), (30, np.float32),
                                      (50, np.float32), (50, np.float64), (64, np.float32), (100, np.float32),
                                      (128, np.float32), (128, np.float64), (200, np.float32), (400, np.float32)])
-@pytest.mark.parametrize("chunk", [5, 48, 64])
-@pytest.mark.parametrize("kernel", [2, 3, 4])
-def test_pipelined_kernel_vs_oracle(k, dtype, chunk, kernel):
-    """sweep_major_v2_kernel (option kernel=2: warp-uniform control flow, full-mask shuffles, one-step
-    register pipeline), sweep_major_v3_kernel (kernel=3: cp.async rings in shared memory, three steps
-    ahead) and sweep_major_v4_kernel (kernel=4: the same with vector-loaded triples; chunk=5 exercises its
-    fall-back to kernel 3) on ragged data with empty rows, chunk lengths that are not multiples of the lane-group width,
+@pytest.mark.parametrize("chunk", [32, 96, 256])
+def test_sweep_kernel_vs_oracle(k, dtype, chunk):
+    """sweep_rows_kernel (cp.async rings three steps ahead, triples staged through shared memory, padded
+    chunks) on ragged data with empty rows, chunk lengths that leave most of the last chunk as padding,
     several L2 panels: 2 iterations vs the fp64 oracle from the same start."""
     nU, nI, nnz = 500, 260, 9000
     u, i, y = O.synth_coo(nU - 40, nI - 30, nnz, seed=k + chunk)     # the last 40 users / 30 items have no data
@@ -480,16 +485,16 @@ def test_pipelined_kernel_vs_oracle(k, dtype, chunk, kernel):
     for _ in range(2):
         O.cavi_full_iteration(ref, y, u, i, **HYP)
     tol = 1e-11 if dtype == np.float64 else 2e-5
-    out = _fit_gpu(y, u, i, nU, nI, k, 2, 11, dtype=dtype, sweep=0, kernel=kernel, panel_mb=0.03, chunk=chunk)
+    out = _fit_gpu(y, u, i, nU, nI, k, 2, 11, dtype=dtype, sweep=0, panel_mb=0.03, chunk=chunk)
     for key in STATE_KEYS:
         assert relerr(out[key], ref[key]) < tol, key
 
 
-@pytest.mark.parametrize("kernel", [2, 3, 4])
-def test_pipelined_kernel_golden_trajectory(golden_full, kernel):
-    """100 full-batch iterations of the README toy with the pipelined kernels vs the compiled reference."""
+@pytest.mark.parametrize("lpg", [0, 8])
+def test_sweep_kernel_golden_trajectory(golden_full, lpg):
+    """100 full-batch iterations of the README toy vs the compiled reference (generic shape and 8 lanes per row)."""
     g = golden_full
     for its, tol in ((1, 1e-12), (10, 1e-11), (100, 1e-9)):
-        out = _fit_gpu(g["Y"], g["ix_u"], g["ix_i"], 100, 100, 10, its, 123, kernel=kernel, chunk=16)
+        out = _fit_gpu(g["Y"], g["ix_u"], g["ix_i"], 100, 100, 10, its, 123, lpg=lpg, chunk=32)
         for key in STATE_KEYS:
             assert relerr(out[key], g["it%d_%s" % (its, key)]) < tol, key

@@ -1,0 +1,174 @@
+"""GPU parity at 1/24 of the headline workload against the COMPILED UNMODIFIED reference (oracle/_ref,
+run on the GPU box's host cores), plus the tiny-shape-prior case the per-row factorisation cannot
+represent without its rescue path.
+
+Sizes: 41 666 x 15 833 users x items, 2 000 000 nnz (H / 24: same generator, same density regime).
+Tolerances:
+  * fp32 engine vs the reference's float build: ONE iteration from the identical start, every state
+    array <= 1e-5 relative (k = 30 / 50 / 128: configs C2 / H / C3);
+  * fp64 engine vs the reference's double build: 5 iterations <= 1e-9 (k = 30 and k = 128);
+  * SVI (config C4's shape scaled by 24: 2 083 users / 833 items per batch), 2 epochs, fp64, the
+    reference with ncores=1 (its only deterministic minibatch mode): <= 1e-9;
+  * a = c = 0.01 on sparse low-degree rows vs the oracle with sum_exp_trick=True: fp64 <= 1e-9,
+    fp32 <= 1e-4 after 2 iterations and finite.
+"""
+import numpy as np
+import pytest
+
+from conftest import STATE_KEYS, relerr
+from oracle import hpf_oracle as O
+from oracle import ref_loader as R
+
+pytestmark = pytest.mark.gpu
+
+NU, NI, NNZ = 41_666, 15_833, 2_000_000
+HYP = dict(a=0.3, a_prime=0.3, b_prime=1.0, c=0.3, c_prime=0.3, d_prime=1.0)
+
+
+@pytest.fixture(scope="module")
+def data():
+    return O.synth_coo(NU, NI, NNZ, seed=42, alpha=0.6)
+
+
+def _cores():
+    import os
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def _fit_gpu_from_loops(u, i, y, k, its, dtype, hyp=HYP, **opts):
+    """Engine run from the product's own initialiser (bit-identical to the reference's, tested on CPU)."""
+    from hpfrec_b200.engine import Engine
+    from hpfrec_b200.loops import CudaLoops
+    rb = np.dtype(dtype).itemsize
+    loops = CudaLoops(rb == 4, device=0)
+    st = loops.initialize_parameters(np.empty((NU, k), dtype), np.empty((NI, k), dtype), 123, hyp["a"], hyp["a_prime"],
+                                     hyp["b_prime"], hyp["c"], hyp["c_prime"], hyp["d_prime"])
+    eng = Engine(NU, NI, k, rb, 0)
+    for name, val in opts.items():
+        eng.set_option(name, val)
+    eng.set_hyper(hyp["a"], hyp["a_prime"], hyp["b_prime"], hyp["c"], hyp["c_prime"], hyp["d_prime"])
+    eng.load_state(*st)
+    eng.load_coo(np.ascontiguousarray(u, np.int64), np.ascontiguousarray(i, np.int64), np.ascontiguousarray(y, dtype))
+    eng.step_full(its)
+    out = eng.export_all()
+    eng.close()
+    return out
+
+
+@pytest.mark.parametrize("k", [30, 50, 128])
+def test_fp32_single_iteration_vs_compiled_reference(data, k):
+    mod = R.load(True)
+    if mod is None:
+        pytest.skip("oracle/_ref not built on this box")
+    u, i, y = data
+    r = R.ref_fit_hpf(mod, y.astype(np.float32), u, i, NU, NI, k, 1, seed=123, ncores=_cores())
+    out = _fit_gpu_from_loops(u, i, y, k, 1, np.float32)
+    for key in STATE_KEYS:
+        assert relerr(out[key], r[key]) < 1e-5, (key, k)
+
+
+@pytest.mark.parametrize("k", [30, 128])
+def test_fp64_five_iterations_vs_compiled_reference(data, k):
+    mod = R.load(False)
+    if mod is None:
+        pytest.skip("oracle/_ref not built on this box")
+    u, i, y = data
+    r = R.ref_fit_hpf(mod, y, u, i, NU, NI, k, 5, seed=123, ncores=_cores())
+    out = _fit_gpu_from_loops(u, i, y, k, 5, np.float64)
+    for key in STATE_KEYS:
+        assert relerr(out[key], r[key]) < 1e-9, (key, k)
+
+
+def test_svi_two_epochs_vs_compiled_reference(data):
+    """Config C4's shape at 1/24: multi-thousand-row minibatches assembled on the device, item epoch then
+    user epoch (pxi:265-273), through the drop-in `fit_hpf` of hpfrec_b200.loops."""
+    mod = R.load(False)
+    if mod is None:
+        pytest.skip("oracle/_ref not built on this box")
+    from hpfrec_b200.loops import CudaLoops
+    u, i, y = data
+    k, upb, ipb = 20, 2083, 833
+    order = np.argsort(u, kind="stable")          # fit() sorts by user for minibatch runs (init:516-521)
+    u, i, y = u[order], i[order], y[order]
+    st_ix_u = np.concatenate([[0], np.cumsum(np.bincount(u, minlength=NU))]).astype(np.uint64)
+    r = R.ref_fit_hpf(mod, y, u, i, NU, NI, k, 2, seed=123, ncores=1, users_per_batch=upb, items_per_batch=ipb,
+                      st_ix_u=st_ix_u)
+    loops = CudaLoops(False, device=0)
+    Theta = np.empty((NU, k))
+    Beta = np.empty((NI, k))
+    niter, temp, _ = loops.fit_hpf(0.3, 0.3, 1.0, 0.3, 0.3, 1.0, y.astype(np.float64), u.astype(np.uint64), i.astype(np.uint64),
+                                   Theta, Beta, 2, "maxiter", 0, 1e-3, upb, ipb, lambda x: 1 / np.sqrt(x + 2), 0, st_ix_u,
+                                   "", 123, 0, 1, 0, 0, np.empty(0), np.empty(0, np.uint64), np.empty(0, np.uint64), 0, 1, 0)
+    got = dict(Theta=Theta, Beta=Beta, Gamma_shp=temp[0], Gamma_rte=temp[1], Lambda_shp=temp[2], Lambda_rte=temp[3],
+               k_rte=temp[4], t_rte=temp[5])
+    assert niter == r["niter"]
+    for key in STATE_KEYS:
+        assert relerr(got[key], r[key]) < 1e-9, key
+
+
+def _sparse_low_degree(seed=7):
+    """Many degree-1/2 users over few items with large counts: with a = c = 0.01 every row's E[log] spreads by
+    ~100 across factors, and most (user, item) pairs have their dominant factors in different columns."""
+    rng = np.random.default_rng(seed)
+    nU, nI = 3000, 400
+    deg = rng.choice([1, 1, 1, 2, 3], size=nU)
+    u = np.repeat(np.arange(nU), deg)
+    i = rng.integers(0, nI, size=u.shape[0])
+    key = np.unique(u * nI + i)
+    u, i = key // nI, key % nI
+    y = (1 + rng.poisson(4.0, size=u.shape[0])).astype(np.float64)
+    return nU, nI, u.astype(np.int64), i.astype(np.int64), y
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-9), (np.float32, 1e-4)])
+@pytest.mark.parametrize("k", [8, 50])
+def test_tiny_shape_priors_need_the_rescue_path(dtype, tol, k):
+    """a = c = 0.01 made the fp32 engine produce inf/NaN where the reference with
+    sum_exp_trick=True stays finite.  The engine now switches its rescue path on by itself for such priors
+    (robust=auto) and must match the max-subtracted reference arithmetic (pxi:560-577)."""
+    nU, nI, u, i, y = _sparse_low_degree()
+    hyp = dict(a=0.01, a_prime=0.3, b_prime=1.0, c=0.01, c_prime=0.3, d_prime=1.0)
+    st0 = O.initialize_parameters(nU, nI, k, 5, hyp["a_prime"], hyp["b_prime"], hyp["c_prime"], hyp["d_prime"], dtype)
+    ref = {k_: v.astype(np.float64) for k_, v in st0.items()}
+    from hpfrec_b200.engine import Engine
+    for its in (1, 2, 6):
+        ref_it = {k_: v.copy() for k_, v in ref.items()}
+        for _ in range(its):
+            O.cavi_full_iteration(ref_it, y, u, i, sum_exp_trick=True, **hyp)
+        for sweep in (0, 1):
+            eng = Engine(nU, nI, k, np.dtype(dtype).itemsize)
+            eng.set_option("sweep", sweep)
+            eng.set_option("chunk", 32)
+            eng.set_hyper(hyp["a"], hyp["a_prime"], hyp["b_prime"], hyp["c"], hyp["c_prime"], hyp["d_prime"])
+            c = lambda x: np.ascontiguousarray(x, dtype=dtype)
+            eng.load_state(c(st0["Gamma_shp"]), c(st0["Gamma_rte"]), c(st0["Lambda_shp"]), c(st0["Lambda_rte"]),
+                           c(st0["k_rte"]), c(st0["t_rte"]))
+            eng.load_coo(u, i, c(y))
+            assert eng.describe()["robust"] == "1"
+            eng.step_full(its)
+            out = eng.export_all()
+            eng.close()
+            for key in STATE_KEYS:
+                assert np.isfinite(out[key]).all(), (key, its, sweep)
+                assert relerr(out[key], ref_it[key]) < (tol if its <= 2 else tol * 30), (key, its, sweep)
+
+
+def test_tiny_shape_priors_minibatch():
+    """The same priors through the minibatch step (partial_fit forces the max-subtracted branch, pxi:438-440)."""
+    nU, nI, u, i, y = _sparse_low_degree(seed=11)
+    k = 12
+    hyp = dict(a=0.01, a_prime=0.3, b_prime=1.0, c=0.01, c_prime=0.3, d_prime=1.0)
+    ref = O.fit_full(y, u, i, nU, nI, k, 3, seed=9, sum_exp_trick=True, **hyp)
+    from hpfrec_b200.engine import Engine
+    eng = Engine(nU, nI, k, 8)
+    eng.set_hyper(hyp["a"], hyp["a_prime"], hyp["b_prime"], hyp["c"], hyp["c_prime"], hyp["d_prime"])
+    eng.load_state(ref["Gamma_shp"], ref["Gamma_rte"], ref["Lambda_shp"], ref["Lambda_rte"], ref["k_rte"], ref["t_rte"])
+    sel = u < 600
+    users, items = np.unique(u[sel]), np.unique(i[sel])
+    eng.step_batch(u[sel], i[sel], y[sel], users, items, True, 0.7, nU / users.shape[0], True)
+    out = eng.export_all()
+    eng.close()
+    O.partial_fit_step(ref, y[sel], u[sel], i[sel], users, items, True, 0.7, nU / users.shape[0], **hyp)
+    for key in STATE_KEYS:
+        assert np.isfinite(out[key]).all(), key
+        assert relerr(out[key], ref[key]) < 1e-9, key

@@ -1,0 +1,162 @@
+#!/usr/bin/env python3
+"""Tuning harness of the full-batch sweep kernel (GPU box).
+
+    python -m hpfrec_b200.build                 (build container)
+    python tools/tune.py [--budget-s 240]       (GPU box, via gpurun)
+
+Dimensions: L2 panel size of the gathered side, lane-group shape (lanes per row, CTA size), L2 policies
+on/off, whole-stride copies (fullrow), chunk length.  EVERY configuration is first checked against the
+single-pass COO kernel's result from the same state (max relative difference of Theta and Beta after 2
+iterations) and only then timed (CUDA events around each kernel, engine option "timing").
+
+Output: gpurun_out/tune.jsonl (one JSON object per configuration), best per workload printed at the end.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from hpfrec_b200.engine import Engine  # noqa: E402
+from hpfrec_b200.loops import CudaLoops  # noqa: E402
+
+T0 = time.time()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--nusers", type=int, default=1_000_000)
+    ap.add_argument("--nitems", type=int, default=380_000)
+    ap.add_argument("--nnz", type=int, default=48_000_000)
+    ap.add_argument("--budget-s", type=float, default=240.0)
+    ap.add_argument("--tiny", action="store_true", help="plumbing check on a small problem")
+    ap.add_argument("--stage", default="all", help="comma list of: k50,k30,k128,f64")
+    a = ap.parse_args()
+    if a.tiny:
+        a.nusers, a.nitems, a.nnz = 20_000, 8_000, 400_000
+    stages = {"k50", "k30", "k128", "f64"} if a.stage == "all" else set(a.stage.split(","))
+    dev = torch.device("cuda", 0)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    out = open(os.path.join(ROOT, "gpurun_out", "tune.jsonl"), "a")
+    u, i, y = bench.synth_coo_torch(a.nusers, a.nitems, a.nnz, dev, alpha=0.6)
+    u, i = u.to(torch.int32).contiguous(), i.to(torch.int32).contiguous()
+    y32, y64 = y.contiguous(), y.to(torch.float64).contiguous()
+    print("data ready %.1f s" % (time.time() - T0), flush=True)
+
+    def spent():
+        return time.time() - T0
+
+    def get_state(k, rb):
+        npdt = np.float32 if rb == 4 else np.float64
+        loops = CudaLoops(rb == 4, device=0)
+        st = loops.initialize_parameters(np.empty((a.nusers, k), npdt), np.empty((a.nitems, k), npdt),
+                                         123, 0.3, 0.3, 1.0, 0.3, 0.3, 1.0)
+        return [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in st]
+
+    class Setup:
+        def __init__(self, k, rb, panel_mb, state):
+            self.k, self.rb, self.panel_mb, self.state = k, rb, panel_mb, state
+            self.eng = Engine(a.nusers, a.nitems, k, rb, 0)
+            self.eng.set_option("panel_mb", panel_mb)
+            self.eng.set_option("strict", 1)
+            self.eng.load_state(*state)
+            self.eng.load_coo(u, i, y32 if rb == 4 else y64)
+            tdt = torch.float32 if rb == 4 else torch.float64
+            self.theta = torch.empty((a.nusers, k), dtype=tdt, device=dev)
+            self.beta = torch.empty((a.nitems, k), dtype=tdt, device=dev)
+
+        def close(self):
+            self.eng.close()
+
+        def run(self, ref, tag, **opts):
+            eng = self.eng
+            rec = dict(tag=tag, k=self.k, rb=self.rb, ld=eng.ld, panel_mb=self.panel_mb, **opts)
+            try:
+                for name, val in opts.items():
+                    eng.set_option(name, val)
+                eng.load_state(*self.state)
+                eng.step_full(2)
+                eng.export_state(Theta=self.theta, Beta=self.beta)
+                if ref is not None:
+                    dth = float(((self.theta - ref[0]).abs() / ref[0].abs().clamp_min(1e-30)).max())
+                    dbe = float(((self.beta - ref[1]).abs() / ref[1].abs().clamp_min(1e-30)).max())
+                    rec["max_rel_diff"] = max(dth, dbe)
+                    tol = 2e-4 if self.rb == 4 else 1e-10
+                    rec["ok"] = bool(rec["max_rel_diff"] < tol and torch.isfinite(self.theta).all())
+                eng.set_option("timing", 1)
+                eng.step_full(4)
+                torch.cuda.synchronize()
+                ms, n = eng.phase_ms()
+                eng.set_option("timing", 0)
+                rec["ms"] = [round(x / n, 4) for x in ms]
+                rec["ms_sweep"] = round((ms[0] + ms[1]) / n, 4)
+                rec["ms_iter"] = round(sum(ms) / n, 4)
+                cfg = eng.describe()
+                rec["panels"] = [int(cfg["panels_item_major"]), int(cfg["panels_user_major"])]
+            except Exception as exc:  # an unknown variant or a failed launch must not stop the sweep
+                rec["error"] = repr(exc)[:300]
+                rec["ok"] = False
+            rec["t"] = round(spent(), 1)
+            out.write(json.dumps(rec) + "\n")
+            out.flush()
+            print(json.dumps(rec), flush=True)
+            if ref is None:
+                return rec, (self.theta.clone(), self.beta.clone())
+            return rec
+
+    results = {}
+
+    def workload(name, k, rb, panels, shapes, budget_frac):
+        if name not in stages:
+            return
+        state = get_state(k, rb)
+        recs = []
+        ref = None
+        for pidx, panel in enumerate(panels):
+            if pidx > 0 and spent() > a.budget_s * budget_frac:
+                print("budget: skipping panel", panel, flush=True)
+                continue
+            try:
+                st = Setup(k, rb, panel, state)
+            except Exception as exc:
+                print("setup failed", name, panel, repr(exc)[:200], flush=True)
+                continue
+            if ref is None:
+                r0, ref = st.run(None, "coo-reference", sweep=1)
+                st.eng.set_option("sweep", 0)
+            for sidx, opts in enumerate(shapes):
+                if pidx > 0 and sidx > 3 and spent() > a.budget_s * budget_frac:
+                    break
+                recs.append(st.run(ref, name, sweep=0, **opts))
+            st.close()
+        good = sorted([r for r in recs if r.get("ok") and "ms_iter" in r], key=lambda r: r["ms_sweep"])
+        results[name] = good[:8]
+
+    def S(lpg, block, hint=1, fullrow=0, chunk=256):
+        return dict(lpg=lpg, block=block, hint=hint, fullrow=fullrow, chunk=chunk)
+
+    workload("k50", 50, 4, [96.0, 64.0, 48.0, 128.0, 1e6, 32.0],
+             [S(4, 128), S(8, 256), S(8, 128), S(4, 64), S(4, 128, hint=0), S(8, 256, hint=0), S(4, 128, fullrow=1),
+              S(8, 256, fullrow=1), S(4, 128, chunk=128), S(4, 128, chunk=512), S(8, 256, chunk=512),
+              S(4, 128, chunk=1024)], 0.55)
+    workload("k30", 30, 4, [96.0, 48.0, 1e6], [S(4, 256), S(4, 128), S(8, 256)], 0.7)
+    workload("k128", 128, 4, [96.0, 48.0, 192.0], [S(8, 128), S(16, 256), S(16, 128), S(8, 64)], 0.85)
+    workload("f64", 50, 8, [96.0, 48.0], [S(16, 128), S(8, 128)], 1.0)
+    print("== best ==")
+    for name, good in results.items():
+        for r in good[:4]:
+            print(name, json.dumps(r), flush=True)
+    json.dump(results, open(os.path.join(ROOT, "gpurun_out", "tune_best.json"), "w"), indent=1)
+    out.close()
+    print("tune done in %.0f s" % spent(), flush=True)
+
+
+if __name__ == "__main__":
+    main()
