@@ -1,19 +1,21 @@
 #!/usr/bin/env python3
 """bench.py -- full-batch CAVI iterations/s on the MillionSong-shaped synthetic (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--config H|C2|C3|H_f64|C4|C5] [--impl reference]
 
 A "step" is one complete full-batch CAVI iteration (the reference's loop body, cython_loops.pxi:230-259)
-over the whole nnz list.  Default workload = H of SURVEY.md §8: 1M x 380K users x items, 48M nnz,
-k=50, fp32.  For N>1 the nnz list is sharded by user range (balanced by nnz) with the item side
-replicated and one all-reduce per iteration; the problem size is fixed, so scaling is "strong".
+over the whole nnz list -- for --config C4 one SVI epoch (cython_loops.pxi:262-377).  Default workload = H
+of SURVEY.md §8: 1M x 380K users x items, 48M nnz, k=50, fp32.  For N>1 the nnz list is sharded by user
+range (balanced by nnz) with the item side replicated and one exchange per iteration; the problem size is
+fixed, so scaling is "strong".
 
 Rank 0 prints ONE JSON line (see the contract in the task description): value = iterations/s from
 device-resident inputs (CUDA events on the engine's stream, barrier + synchronize on both sides, max
 over ranks); `e2e` = the same iterations through the C ABI with HOST (pinned) buffers: upload of state
 and triples, index build, K iterations, download of the eight result arrays, all inside the timed
-region; `roofline` against MEASURED_PEAKS.json; `cpu_baseline` = the compiled, unmodified reference
-(oracle/_ref) timed on this box's host cores on a bounded sample.
+region; `roofline` = SURVEY §8(d)'s algorithmic bytes of one iteration / device time per iteration against
+MEASURED_PEAKS.json; `cpu_baseline` = the compiled, unmodified reference (oracle/_ref) timed on this
+box's host cores on a bounded sample.  `--impl reference` times that reference on the FULL configuration.
 """
 import argparse
 import json
@@ -32,6 +34,17 @@ if ROOT not in sys.path:
 METRIC = "full_batch_cavi_iterations_per_s"
 UNIT = "iterations/s"
 
+# BASELINE.json configs (SURVEY §8 preamble): shapes, row length, arithmetic type, minibatch sizes
+CONFIGS = {
+    "H": dict(nusers=1_000_000, nitems=380_000, nnz=48_000_000, k=50, dtype="f32"),
+    "C2": dict(nusers=1_000_000, nitems=380_000, nnz=48_000_000, k=30, dtype="f32"),
+    "C3": dict(nusers=1_000_000, nitems=380_000, nnz=48_000_000, k=128, dtype="f32"),
+    "H_f64": dict(nusers=1_000_000, nitems=380_000, nnz=48_000_000, k=50, dtype="f64"),
+    "C4": dict(nusers=1_000_000, nitems=380_000, nnz=48_000_000, k=50, dtype="f32", users_per_batch=50_000,
+               items_per_batch=20_000),
+    "C5": dict(nusers=10_000_000, nitems=1_000_000, nnz=500_000_000, k=50, dtype="f32"),
+}
+
 
 # -----------------------------------------------------------------------------------------------------
 def parse_args():
@@ -40,22 +53,49 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--nusers", type=int, default=1_000_000)
-    ap.add_argument("--nitems", type=int, default=380_000)
-    ap.add_argument("--nnz", type=int, default=48_000_000)
-    ap.add_argument("--k", type=int, default=50)
-    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--config", default=None, choices=sorted(CONFIGS), help="a BASELINE.json configuration (default H)")
+    ap.add_argument("--nusers", type=int, default=None)
+    ap.add_argument("--nitems", type=int, default=None)
+    ap.add_argument("--nnz", type=int, default=None)
+    ap.add_argument("--k", type=int, default=None)
+    ap.add_argument("--dtype", default=None, choices=["f32", "f64"])
+    ap.add_argument("--users-per-batch", type=int, default=None)
+    ap.add_argument("--items-per-batch", type=int, default=None)
     ap.add_argument("--alpha", type=float, default=0.6, help="Zipf exponent of item popularity")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-div", type=int, default=24, help="CPU sample = workload / this")
+    ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--cpu-sample-div", type=int, default=8, help="cpu_baseline sample = workload / this")
+    ap.add_argument("--ref-sample-div", type=int, default=1,
+                    help="--impl reference: 1 = the full configuration (default); >1 times workload / this and says so")
+    ap.add_argument("--init", default=None, choices=["host", "device"],
+                    help="random start: host = the reference's numpy MT19937 stream (default), device = torch generator "
+                         "(default for C5, whose host start is 4.4 GB per rank)")
     ap.add_argument("--option", action="append", default=[], help="engine option name=value")
-    return ap.parse_args()
+    a = ap.parse_args()
+    base = dict(CONFIGS[a.config or "H"])
+    for key in ("nusers", "nitems", "nnz", "k", "dtype"):
+        if getattr(a, key) is None:
+            setattr(a, key, base[key])
+    if a.users_per_batch is None:
+        a.users_per_batch = base.get("users_per_batch", 0)
+    if a.items_per_batch is None:
+        a.items_per_batch = base.get("items_per_batch", 0)
+    a.config_name = a.config or ("H" if all(getattr(a, k_) == CONFIGS["H"][k_] for k_ in CONFIGS["H"]) else "custom")
+    if a.init is None:
+        a.init = "device" if a.nusers * a.k > 200_000_000 else "host"
+    return a
 
 
-def workload_name(a):
-    return "%dx%d users x items, %d nnz, k=%d, %s full-batch CAVI (synthetic: lognormal users, Zipf(%.1f) items)" % (
-        a.nusers, a.nitems, a.nnz, a.k, "fp32" if a.dtype == "f32" else "fp64", a.alpha)
+def workload_name(a, div=1):
+    nU, nI, nnz = a.nusers // div, a.nitems // div, a.nnz // div
+    kind = "full-batch CAVI" if not (a.users_per_batch or a.items_per_batch) else \
+        "SVI epochs (%d users / %d items per batch)" % (a.users_per_batch, a.items_per_batch)
+    name = "%s: %dx%d users x items, %d nnz, k=%d, %s %s (synthetic: lognormal users, Zipf(%.1f) items)" % (
+        a.config_name, nU, nI, nnz, a.k, "fp32" if a.dtype == "f32" else "fp64", kind, a.alpha)
+    if div != 1:
+        name += " [SAMPLE: workload / %d]" % div
+    return name
 
 
 # -----------------------------------------------------------------------------------------------------
@@ -147,36 +187,8 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-# -----------------------------------------------------------------------------------------------------
-def cpu_reference_rate(a, steps, warmup, verbose=False):
-    """Times the compiled UNMODIFIED reference (oracle/_ref: hpfrec.cython_loops_float.fit_hpf, all host
-    threads, deterministic scatter) on a bounded sample of the workload.  The CPU path is compute-bound
-    on psi/log/exp per (nnz, factor), so nnz/s is size-independent and the sample rate
-    extrapolates to the full nnz list.  Returns dict or None if oracle/_ref is absent."""
-    from oracle import ref_loader as R
-    from oracle import hpf_oracle as O
-    use_float = a.dtype == "f32"
-    mod = R.load(use_float)
-    if mod is None:
-        return None
-    div = max(1, a.cpu_sample_div)
-    nU, nI, nnz = max(64, a.nusers // div), max(64, a.nitems // div), max(1024, a.nnz // div)
-    u, i, y = O.synth_coo(nU, nI, nnz, seed=42, alpha=a.alpha)
+def cpu_info():
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    dt = np.float32 if use_float else np.float64
-
-    def run(iters):
-        t0 = time.time()
-        R.ref_fit_hpf(mod, y.astype(dt), u, i, nU, nI, a.k, iters, seed=123, ncores=cores, par_sh=0)
-        return time.time() - t0
-
-    t_base = run(1)                      # init + phi allocation + 1 iteration
-    if warmup > 0:
-        run(1)
-    n_it = max(1, min(steps, 3))
-    t_more = run(1 + n_it)
-    s_per_iter = max(1e-9, (t_more - t_base) / n_it)
-    nnz_per_s = nnz / s_per_iter
     model = ""
     try:
         for line in open("/proc/cpuinfo"):
@@ -185,33 +197,124 @@ def cpu_reference_rate(a, steps, warmup, verbose=False):
                 break
     except Exception:
         pass
-    return {"nnz_per_s": nnz_per_s, "iters_per_s_full_workload": nnz_per_s / a.nnz, "cores": cores,
-            "cpu_model": model, "s_per_iter_sample": s_per_iter,
-            "sample": "%dx%d, %d nnz (workload/%d, same generator), k=%d, %s, (t[maxiter=%d]-t[maxiter=1])/%d"
-                      % (nU, nI, nnz, div, a.k, "fp32" if use_float else "fp64", 1 + n_it, n_it)}
+    return cores, model
+
+
+def host_triples(a, div):
+    """The workload's triples on the host.  Generated on the GPU when there is one (identical to the data of
+    the GPU arm), else with the numpy generator of the oracle (same recipe, slower)."""
+    nU, nI, nnz = max(64, a.nusers // div), max(64, a.nitems // div), max(1024, a.nnz // div)
+    try:
+        import torch
+        if torch.cuda.is_available():
+            u, i, y = synth_coo_torch(nU, nI, nnz, torch.device("cuda", 0), seed=42, alpha=a.alpha)
+            out = (u.cpu().numpy(), i.cpu().numpy(), y.cpu().numpy().astype(np.float64))
+            del u, i, y
+            torch.cuda.empty_cache()
+            return nU, nI, nnz, out, "torch generator on the GPU (the GPU arm's data)"
+    except Exception:
+        pass
+    from oracle import hpf_oracle as O
+    return nU, nI, nnz, O.synth_coo(nU, nI, nnz, seed=42, alpha=a.alpha), "numpy generator (oracle.synth_coo)"
+
+
+# -----------------------------------------------------------------------------------------------------
+def cpu_reference_rate(a, warm_iters, timed_iters, div):
+    """Times the compiled UNMODIFIED reference (oracle/_ref: hpfrec.cython_loops_{float,double}.fit_hpf, all host
+    threads, deterministic scatter) on the workload / div.  Two calls: fit_hpf(maxiter=warm_iters) and
+    fit_hpf(maxiter=warm_iters+timed_iters); both pay the same initialisation and phi allocation, so their
+    difference is `timed_iters` iterations.  Returns dict or None if oracle/_ref is absent."""
+    from oracle import ref_loader as R
+    use_float = a.dtype == "f32"
+    mod = R.load(use_float)
+    if mod is None:
+        return None
+    nU, nI, nnz, (u, i, y), gen = host_triples(a, div)
+    cores, model = cpu_info()
+    dt = np.float32 if use_float else np.float64
+    y = y.astype(dt)
+    upb, ipb = a.users_per_batch // div, a.items_per_batch // div
+    st_ix_u = None
+    ncores = cores
+    if upb or ipb:   # SVI: data sorted by user + CSR pointer (init:516-521); only ncores=1 is deterministic
+        order = np.argsort(u, kind="stable")
+        u, i, y = u[order], i[order], y[order]
+        st_ix_u = np.concatenate([[0], np.cumsum(np.bincount(u, minlength=nU))]).astype(np.uint64)
+
+    def run(iters):
+        t0 = time.time()
+        R.ref_fit_hpf(mod, y, u, i, nU, nI, a.k, iters, seed=123, ncores=ncores, par_sh=0, users_per_batch=upb,
+                      items_per_batch=ipb, st_ix_u=st_ix_u)
+        return time.time() - t0
+
+    warm_iters = max(1, warm_iters)
+    t_warm = run(warm_iters)
+    t_all = run(warm_iters + timed_iters)
+    s_per_iter = max(1e-9, (t_all - t_warm) / timed_iters)
+    return {"s_per_iter": s_per_iter, "nnz_per_s": nnz / s_per_iter, "cores": cores, "cpu_model": model,
+            "seconds_warm_call": t_warm, "seconds_timed_call": t_all, "nU": nU, "nI": nI, "nnz": nnz,
+            "data": gen,
+            "sample": "%dx%d, %d nnz (workload/%d), k=%d, %s, (t[maxiter=%d]-t[maxiter=%d])/%d, %d threads"
+                      % (nU, nI, nnz, div, a.k, "fp32" if use_float else "fp64", warm_iters + timed_iters, warm_iters,
+                         timed_iters, ncores)}
 
 
 def run_reference(a):
+    """The reference arm: the reference's own CPU implementation, its stock entry point (fit_hpf, pxi:147), all
+    host threads, on the SAME configuration as the GPU arm (unless --ref-sample-div says otherwise): W warm-up
+    iterations in one call, then W+K in a second; ms_per_step = their difference / K."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    res = cpu_reference_rate(a, a.steps, a.warmup)
+    div = max(1, a.ref_sample_div)
+    res = cpu_reference_rate(a, a.warmup, a.steps, div)
     if res is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built on this box"}))
         return
-    v = res["iters_per_s_full_workload"]
+    v = 1.0 / res["s_per_iter"]
+    note = "the full configuration" if div == 1 else "a 1/%d sample of the configuration (labelled in config.workload)" % div
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus,
-            "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * res["s_per_iter"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
-            "config": {"workload": workload_name(a)}, "nnz_per_s": res["nnz_per_s"],
+            "config": {"workload": workload_name(a, div), "what": "compiled unmodified reference on " + note,
+                       "data_generator": res["data"]},
+            "nnz_per_s": res["nnz_per_s"],
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": res["cores"], "kind": "reference",
-                             "sample": res["sample"], "cpu_model": res["cpu_model"]},
+                             "sample": res["sample"], "cpu_model": res["cpu_model"],
+                             "seconds_warm_call": res["seconds_warm_call"], "seconds_timed_call": res["seconds_timed_call"],
+                             "build": "oracle/build_ref.py: gcc -O2 -fopenmp -march=x86-64-v3 (the reference's setup.py uses "
+                                      "-march=native -flto); the serial scatter bounds it, 16 and 32 threads give the same rate"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
 
 
 # -----------------------------------------------------------------------------------------------------
+def initial_state(a, loops, lo, hi, dev):
+    """(Gamma_shp, Gamma_rte, Lambda_shp, Lambda_rte, k_rte, t_rte) for users [lo, hi) and all items."""
+    import torch
+    nU, nI, k = a.nusers, a.nitems, a.k
+    npdt = np.float32 if a.dtype == "f32" else np.float64
+    if a.init == "host":
+        Theta = np.empty((nU, k), npdt)
+        Beta = np.empty((nI, k), npdt)
+        Gs, Gr, Ls, Lr, kr, tr = loops.initialize_parameters(Theta, Beta, 123, 0.3, 0.3, 1.0, 0.3, 0.3, 1.0)
+        del Theta, Beta
+        return [np.ascontiguousarray(x[lo:hi]) for x in (Gs, Gr)] + [Ls, Lr, np.ascontiguousarray(kr[lo:hi]), tr]
+    # device start (same distribution as pxi:134-138: prior + 0.01 U; NOT the reference's bit stream)
+    tdt = torch.float32 if a.dtype == "f32" else torch.float64
+    g = torch.Generator(device=dev)
+    g.manual_seed(123)
+    Lr = 0.3 + 0.01 * torch.rand((nI, k), generator=g, device=dev, dtype=tdt)
+    Ls = 0.3 + 0.01 * torch.rand((nI, k), generator=g, device=dev, dtype=tdt)
+    g.manual_seed(1000 + lo)
+    Gr = 0.3 + 0.01 * torch.rand((hi - lo, k), generator=g, device=dev, dtype=tdt)
+    Gs = 0.3 + 0.01 * torch.rand((hi - lo, k), generator=g, device=dev, dtype=tdt)
+    kr = torch.ones((hi - lo, 1), device=dev, dtype=tdt)
+    tr = torch.ones((nI, 1), device=dev, dtype=tdt)
+    return [Gs, Gr, Ls, Lr, kr, tr]
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -227,9 +330,20 @@ def run_ours(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     rb = 4 if a.dtype == "f32" else 8
-    npdt = np.float32 if rb == 4 else np.float64
     tdt = torch.float32 if rb == 4 else torch.float64
     nU, nI, nnz, k = a.nusers, a.nitems, a.nnz, a.k
+    svi = bool(a.users_per_batch or a.items_per_batch)
+    if svi and world > 1:
+        raise SystemExit("the SVI configuration (C4) is single-GPU by specification (SURVEY §8e)")
+    options = {}
+    for opt in a.option:
+        name, val = opt.split("=")
+        options[name] = float(val)
+
+    # ---- multi-GPU: prove the sharded data plane before timing it -----------------------------------
+    parity = None
+    if world > 1 and not a.no_parity_check:
+        parity = hdist.sharded_parity_check(local, options=options)
 
     # ---- synthetic inputs, identical on every rank; each rank keeps its user range ---------------
     u, i, y = synth_coo_torch(nU, nI, nnz, dev, seed=42, alpha=a.alpha)
@@ -237,60 +351,52 @@ def run_ours(a):
     cuts = hdist.plan_user_shards(u, nU, world)
     lo, hi = cuts[rank], cuts[rank + 1]
     lu, li, ly = hdist.shard_triples(u, i, y, lo, hi)
-    lu, li, ly = lu.contiguous(), li.contiguous(), ly.contiguous()
+    lu, li, ly = lu.to(torch.int32).contiguous(), li.to(torch.int32).contiguous(), ly.contiguous()
     del u, i, y
     torch.cuda.empty_cache()
     loops = CudaLoops(rb == 4, device=local)
-    Theta = np.empty((nU, k), npdt)
-    Beta = np.empty((nI, k), npdt)
-    Gs, Gr, Ls, Lr, kr, tr = loops.initialize_parameters(Theta, Beta, 123, 0.3, 0.3, 1.0, 0.3, 0.3, 1.0)
-    del Theta, Beta
-    Gs, Gr, kr = (np.ascontiguousarray(x[lo:hi]) for x in (Gs, Gr, kr))
+    state = initial_state(a, loops, lo, hi, dev)
     nUl = hi - lo
+    nnz_local = int(lu.shape[0])
 
     stream = torch.cuda.current_stream()
     eng = Engine(nUl, nI, k, rb, local)
-    for opt in a.option:
-        name, val = opt.split("=")
-        eng.set_option(name, float(val))
+    if svi:
+        eng.set_option("panel_mb", 1e9)   # minibatches are assembled from plain CSR / CSC orderings
+    for name, val in options.items():
+        eng.set_option(name, val)
     eng.set_hyper(0.3, 0.3, 1.0, 0.3, 0.3, 1.0)
-    eng.load_state(Gs, Gr, Ls, Lr, kr, tr)
+    runner = None
+    if world > 1:
+        runner = hdist.ShardedLoop(eng, mode=os.environ.get("HPF_MULTI", "auto"), graph=os.environ.get("HPF_GRAPH", "1") == "1")
+        stream = runner.stream
+    eng.load_state(*state)
     eng.load_coo(lu, li, ly)
     ld = eng.ld
     engine_config = eng.describe()
+    if runner is not None:
+        engine_config["exchange"] = runner.mode
 
-    if world > 1:
-        partial = hdist.engine_partial_tensors(eng, local)
+    svi_state = None
+    if svi:
+        svi_state = dict(rng=np.random.default_rng(123), users=np.arange(nU, dtype=np.int64),
+                         items=np.arange(nI, dtype=np.int64), epoch=0)
 
-        mode = os.environ.get("HPF_MULTI", "peer")
-        graphed = None
-        if os.environ.get("HPF_GRAPH", "0") == "1":
-            graphed = hdist.GraphedShardLoop(eng, mode)
-            stream = graphed.stream
-        elif mode == "peer":
-            hdist.attach_peers(eng)
-
-        def steps(n):
-            if graphed is not None:
-                with torch.cuda.stream(graphed.stream):
-                    graphed.run(n)
-            elif mode == "plain":
-                hdist.run_sharded_iterations(eng, n, partial)
-            elif mode == "overlap":
-                hdist.run_sharded_iterations_overlapped(eng, n, partial)
-            else:
-                hdist.run_sharded_iterations_peer(eng, n)
-    else:
-        def steps(n):
+    def steps(n):
+        if svi:
+            loops.svi_epochs(eng, svi_state, n, nU, nI, a.users_per_batch, a.items_per_batch)
+        elif runner is not None:
+            runner.run(n)
+        else:
             eng.step_full(n)
-
-    if world == 1:
-        graphed = None
 
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def launches_so_far():
+        return eng.launch_count + (runner.replayed_launches if runner is not None else 0)
 
     # ---- warm-up, then EXACTLY K timed steps ----------------------------------------------------------
     steps(max(a.warmup, 3))
@@ -301,14 +407,14 @@ def run_ours(a):
         time.sleep(0.3)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
-    l0 = eng.launch_count + (graphed.replayed_launches if world > 1 and graphed is not None else 0)
+    l0 = launches_so_far()
     t_wall0 = time.time()
     ev0.record(stream)
     steps(a.steps)
     ev1.record(stream)
     sync_all()
     t_wall1 = time.time()
-    launches = eng.launch_count + (graphed.replayed_launches if world > 1 and graphed is not None else 0) - l0
+    launches = launches_so_far() - l0
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -322,7 +428,7 @@ def run_ours(a):
 
     # ---- per-kernel split (separate profiled pass: events between kernels serialise iterations) ------
     phases = None
-    if world == 1:
+    if world == 1 and not svi:
         eng.set_option("timing", 1)
         eng.step_full(max(3, min(a.steps, 10)))
         torch.cuda.synchronize()
@@ -331,45 +437,56 @@ def run_ours(a):
         if pn > 0:
             phases = [x / pn for x in pm]
 
-    out_state = None
     e2e = None
-    if not a.no_e2e:
+    if not a.no_e2e and not svi:
         # ---- end to end through the C ABI with HOST buffers (pinned): every call uploads state + triples,
         # builds the orderings, runs K iterations and downloads the eight result arrays.
-        hu = lu.to(torch.int32).cpu().pin_memory().numpy()
-        hi_ = li.to(torch.int32).cpu().pin_memory().numpy()
+        hu = lu.cpu().pin_memory().numpy()
+        hi_ = li.cpu().pin_memory().numpy()
         hy = ly.cpu().pin_memory().numpy()
-        pinned = [torch.from_numpy(x).pin_memory() for x in (Gs, Gr, Ls, Lr, kr, tr)]
-        hstate = [t.numpy() for t in pinned]
+        hstate = [(t if isinstance(t, torch.Tensor) else torch.from_numpy(t)).cpu().pin_memory().numpy() for t in state]
         outs = dict(Gamma_shp=(nUl, k), Gamma_rte=(nUl, k), Lambda_shp=(nI, k), Lambda_rte=(nI, k),
                     k_rte=(nUl, 1), t_rte=(nI, 1), Theta=(nUl, k), Beta=(nI, k))
         out_pinned = {key: torch.empty(shape, dtype=tdt).pin_memory() for key, shape in outs.items()}
         out_state = {key: t.numpy() for key, t in out_pinned.items()}
+        if runner is not None:
+            runner.close()
         eng.close()
-        del lu, li, ly
+        del lu, li, ly, state
         torch.cuda.empty_cache()
         h2d = hu.nbytes + hi_.nbytes + hy.nbytes + sum(x.nbytes for x in hstate)
         d2h = sum(x.nbytes for x in out_state.values())
 
-        def e2e_call():
+        def e2e_call(legs=None):
+            t = [time.time()]
+
+            def lap():
+                if legs is not None:
+                    torch.cuda.synchronize()
+                    t.append(time.time())
             e = Engine(nUl, nI, k, rb, local)
-            for opt in a.option:
-                name, val = opt.split("=")
-                e.set_option(name, float(val))
+            for name, val in options.items():
+                e.set_option(name, val)
             e.set_hyper(0.3, 0.3, 1.0, 0.3, 0.3, 1.0)
+            r = hdist.ShardedLoop(e, mode=os.environ.get("HPF_MULTI", "auto"), graph=False) if world > 1 else None
+            lap()
             e.load_state(*hstate)
+            lap()
             e.load_coo(hu, hi_, hy)
-            if world > 1 and os.environ.get("HPF_MULTI", "peer") == "peer":
-                hdist.attach_peers(e)
-                hdist.run_sharded_iterations_peer(e, a.steps)
-            elif world > 1:
-                hdist.run_sharded_iterations_overlapped(e, a.steps, hdist.engine_partial_tensors(e, local))
+            lap()
+            if r is not None:
+                r.run(a.steps)
             else:
                 e.step_full(a.steps)
+            lap()
             e.export_state(**out_state)
-            n_l = e.launch_count
+            lap()
+            if r is not None:
+                r.close()
             e.close()
-            return n_l
+            if legs is not None:
+                for name, j in (("create_ms", 0), ("load_state_ms", 1), ("load_coo_ms", 2), ("iterate_ms", 3), ("export_ms", 4)):
+                    legs[name] = round(1e3 * (t[j + 1] - t[j]), 2)
 
         e2e_call()  # warm-up (allocator, page-locking paths)
         sync_all()
@@ -380,12 +497,17 @@ def run_ours(a):
         if world > 1:
             dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
         t_e2e = float(t_e2e.item())
+        legs = {}
+        e2e_call(legs)   # a third call with a synchronize between the legs: where the time goes
         e2e = {"value": a.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d * world / a.steps),
                "d2h_bytes_per_step": int(d2h * world / a.steps), "seconds_per_call": t_e2e,
-               "iterations_per_call": a.steps,
+               "iterations_per_call": a.steps, "breakdown_rank0": legs,
                "what": "hpf_create+load_state+load_coo(host pinned)+%d iterations+export_state(host) per call; "
-                       "bytes are per call / iterations, summed over ranks" % a.steps}
+                       "bytes are per call / iterations, summed over ranks; breakdown from a separate call with a "
+                       "device synchronize after every leg" % a.steps}
     else:
+        if runner is not None:
+            runner.close()
         eng.close()
 
     if rank != 0:
@@ -393,89 +515,72 @@ def run_ours(a):
             dist.destroy_process_group()
         return
 
-    # ---- roofline (whole iteration and dominant kernel) ---------------------------------------------------
+    # ---- roofline: SURVEY §8(d) algorithmic bytes of ONE iteration on one GPU / device time per iteration --
     peak, peak_src = measured_peak()
-    nnz_local_max = nnz / world  # shards are nnz-balanced
-    b_iter = algorithmic_bytes(nUl, nI, nnz_local_max, k, rb)      # per GPU (item side replicated)
+    b_iter = algorithmic_bytes(nUl, nI, nnz_local, k, rb)      # per GPU (item side replicated)
     achieved = b_iter / (ms_per_step * 1e-3) / 1e9
-    iteration = {"achieved": achieved, "frac": achieved / peak,
-                 "algorithmic_bytes_per_iteration_per_gpu": int(b_iter), "bytes_per_nnz": b_iter / nnz_local_max,
-                 "what": "whole iteration (2 sweep passes + 2 row updates): nnz*(4+4+s)+4*(nU+nI)*k*s bytes / device ms"}
+    wl_key = "%dx%dx%d k=%d %s" % (nU, nI, nnz, k, a.dtype)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "whole iteration", "iteration": iteration}
+                "traffic": None, "peak_source": peak_src,
+                "kernel": "whole iteration: 2 x sweep_rows_kernel + 2 x update_rows_kernel" if not svi else
+                          "whole SVI epoch (all minibatches)",
+                "algorithmic_bytes_per_iteration_per_gpu": int(b_iter), "bytes_per_nnz": b_iter / max(1, nnz_local),
+                "what": "SURVEY §8(d): nnz*(4+4+s) + 4*(nU+nI)*k*s bytes per iteration / device ms per iteration"}
     if phases is not None:
-        s = rb
-        sweep_kernel = engine_config.get("kernel", "sweep kernel")
-        # per-launch algorithmic bytes of one pass: triples once + own x read + gathered x read once + sums written
-        pass_bytes = [nnz * (4 + 4 + s) + (2 * nI + nUl) * k * s, nnz * (4 + 4 + s) + (2 * nUl + nI) * k * s]
-        # a one-pass (fused) sweep streams the triples once and touches all four factor / sum matrices once
-        fused_bytes = nnz * (4 + 4 + s) + 2 * (nUl + nI) * k * s
-        upd_bytes = [4 * nUl * k * s, 4 * nI * k * s]  # x r/w, sums r/w(zero) (lean iteration)
         tot = sum(phases)
-        live = [j for j in (0, 1) if phases[j] > 0.02]  # a fused sweep leaves the other pass's slot empty
-        kernels = []
-        for j in live:
-            nbytes = pass_bytes[j] if len(live) == 2 else fused_bytes
-            label = ("item-major pass", "user-major pass")[j] if len(live) == 2 else "one fused %s pass" % ("item-major", "user-major")[j]
-            kernels.append({"name": "%s (%s)" % (sweep_kernel, label), "ms": phases[j], "share": phases[j] / tot,
-                            "algorithmic_bytes": int(nbytes), "achieved_gbs": nbytes / (phases[j] * 1e-3) / 1e9,
-                            "frac": nbytes / (phases[j] * 1e-3) / 1e9 / peak})
-        for j, nm in ((2, "update_rows_kernel (users)"), (3, "update_rows_kernel (items)")):
-            kernels.append({"name": nm, "ms": phases[j], "share": phases[j] / tot, "algorithmic_bytes": int(upd_bytes[j - 2]),
-                            "achieved_gbs": upd_bytes[j - 2] / (phases[j] * 1e-3) / 1e9,
-                            "frac": upd_bytes[j - 2] / (phases[j] * 1e-3) / 1e9 / peak})
-        roofline["kernels"] = kernels
-        # the contract's roofline object describes the DOMINANT kernel, per launch
-        dom = kernels[:len(live)]
-        dom_bytes = sum(kk["algorithmic_bytes"] for kk in dom) / len(dom)
-        dom_ms = sum(kk["ms"] for kk in dom) / len(dom)
-        dom_achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
-        roofline.update({"kernel": "%s (%d launch%s per iteration; per-launch averages)" % (
-                             sweep_kernel, len(dom), "es" if len(dom) > 1 else ""),
-                         "achieved": dom_achieved, "frac": dom_achieved / peak,
-                         "algorithmic_bytes_per_launch": int(dom_bytes), "ms_per_launch": dom_ms,
-                         "share_of_step": sum(kk["ms"] for kk in dom) / tot})
-        try:  # measured DRAM bytes per launch of that kernel from the committed ncu capture (same workload + kernel only)
+        names = ("sweep_rows_kernel (item-major pass)", "sweep_rows_kernel (user-major pass)",
+                 "update_rows_kernel (users)", "update_rows_kernel (items)")
+        roofline["kernels"] = [{"name": nm, "ms": phases[j], "share_of_step": phases[j] / tot} for j, nm in enumerate(names)]
+        roofline["dominant_kernel"] = {"name": "sweep_rows_kernel", "launches_per_iteration": 2,
+                                       "ms_per_launch": (phases[0] + phases[1]) / 2,
+                                       "share_of_step": (phases[0] + phases[1]) / tot}
+        try:  # measured DRAM bytes per iteration from the committed ncu capture (same workload + configuration only)
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            if tr.get("workload") == "%dx%dx%d k=%d %s" % (nU, nI, nnz, k, a.dtype) and tr.get("kernel") == sweep_kernel:
-                sw = tr["sweep_launches"]
-                roofline["traffic"] = int(sum(v["dram_read_bytes"] + v["dram_write_bytes"] for v in sw) / len(sw))
-                roofline["traffic_source"] = "profiles/traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch)"
+            if tr.get("workload") == wl_key:
+                roofline["traffic"] = int(tr["dram_bytes_per_sweep_launch"])
+                roofline["traffic_per_iteration"] = int(tr["dram_bytes_per_iteration"])
+                roofline["traffic_over_algorithmic"] = tr["dram_bytes_per_iteration"] / b_iter
+                roofline["traffic_source"] = tr.get("source")
         except Exception:
             pass
         try:  # the measured ceiling of the bare row-gather pattern (tools/gather_probe.cu), for context
             gc = json.load(open(os.path.join(ROOT, "profiles", "gather_ceiling.json")))
-            if gc.get("workload") == "%dx%dx%d k=%d %s" % (nU, nI, nnz, k, a.dtype):
-                roofline["gather_ceiling"] = {"ms_per_pass": gc["ms_per_pass"], "frac_of_ceiling": gc["ms_per_pass"] / dom_ms,
+            if gc.get("workload") == wl_key:
+                roofline["gather_ceiling"] = {"ms_per_pass": gc["ms_per_pass"],
+                                              "frac_of_ceiling": gc["ms_per_pass"] / roofline["dominant_kernel"]["ms_per_launch"],
                                               "source": gc["source"]}
         except Exception:
             pass
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+    metric, unit = (METRIC, UNIT) if not svi else ("svi_epochs_per_s", "epochs/s")
+    line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
             "config": {"workload": workload_name(a), "parallelism": "user-sharded x%d, item side replicated%s" % (
-                           world, "" if world == 1 else ", exchange=" + os.environ.get("HPF_MULTI", "peer")),
+                           world, "" if world == 1 else ", exchange=" + runner.mode),
                        "l2": "inputs larger than L2 (triples %.2f GB + factors %.2f GB per GPU)" % (
-                           2 * 12 * nnz_local_max / 1e9, 4 * (nUl + nI) * ld * rb / 1e9),
+                           2 * (8 + rb) * nnz_local / 1e9, 4 * (nUl + nI) * ld * rb / 1e9),
                        "timing": "CUDA events on the engine stream, barrier+synchronize both sides, max over ranks",
+                       "init": a.init,
                        "materialize": "shape/rate matrices stored on the last iteration of each call; "
-                                      "intermediate iterations keep the equivalent per-row factors" if world == 1
-                                      else "every iteration"},
+                                      "intermediate iterations keep the equivalent per-row factors"},
             "nnz_per_s": value * nnz, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "engine": engine_config}
+    if parity is not None:
+        line["parity_check"] = parity
     if e2e is not None:
         line["e2e"] = e2e
-    if not a.no_cpu_baseline:
+    if not a.no_cpu_baseline and not svi:
         try:
-            cb = cpu_reference_rate(a, 3, 1)
+            cb = cpu_reference_rate(a, 1, 3, max(1, a.cpu_sample_div))
         except Exception as exc:  # never lose the GPU line to a CPU-side failure
             cb = None
             line["cpu_baseline_error"] = repr(exc)
         if cb is not None:
-            line["cpu_baseline"] = {"value": cb["iters_per_s_full_workload"], "unit": UNIT, "cores": cb["cores"],
-                                    "kind": "reference", "sample": cb["sample"], "nnz_per_s": cb["nnz_per_s"],
-                                    "cpu_model": cb["cpu_model"]}
+            line["cpu_baseline"] = {"value": cb["nnz_per_s"] / a.nnz, "unit": UNIT, "cores": cb["cores"], "kind": "reference",
+                                    "sample": cb["sample"], "nnz_per_s": cb["nnz_per_s"], "cpu_model": cb["cpu_model"],
+                                    "note": "nnz/s of the sample scaled to the workload's nnz (the CPU path is compute-bound "
+                                            "per (nnz, factor)); `bench.py --impl reference` times the full configuration"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -174,6 +174,7 @@ class HPF:
 
         self.Theta = None
         self.Beta = None
+        self._scorer_obj, self._scorer_key = None, None
         self.user_mapping_ = None
         self.item_mapping_ = None
         self.user_dict_ = None
@@ -188,6 +189,30 @@ class HPF:
         """The float or double instantiation of the GPU hot path (the reference picks between its two
         compiled modules the same way at every call site, e.g. hpfrec/__init__.py:508)."""
         return cuda_loops_float if self.use_float else cuda_loops_double
+
+    # ---- device-resident factors for predict / topN / eval_llk ---------------------------------------
+    def _scorer(self):
+        """Theta and Beta on the device, uploaded once per fitted state (they are re-uploaded only after a call
+        that changes them: fit, partial_fit, add_user).  The reference reads its host arrays directly
+        (hpfrec/__init__.py:1277-1291, 1338-1396, 1433); here the same reads are device gathers."""
+        from .engine import Scorer
+        key = (id(self.Theta), id(self.Beta), self.Theta.shape, self.Beta.shape)
+        if getattr(self, "_scorer_obj", None) is None or getattr(self, "_scorer_key", None) != key:
+            self._drop_scorer()
+            self._scorer_obj = Scorer(self.Theta, self.Beta, device=self._loops.device)
+            self._scorer_key = key
+        return self._scorer_obj
+
+    def _drop_scorer(self):
+        obj = getattr(self, "_scorer_obj", None)
+        if obj is not None:
+            obj.close()
+        self._scorer_obj, self._scorer_key = None, None
+
+    def __getstate__(self):   # the device handle does not pickle (the reference pickles with dill, README.md:162-173)
+        state = dict(self.__dict__)
+        state["_scorer_obj"], state["_scorer_key"] = None, None
+        return state
 
     def _typed(self, frame):
         """Count -> real_t, ids -> the reference's index type (reference __init__.py:508-514)."""
@@ -229,6 +254,7 @@ class HPF:
             self.user_dict_ = {self.user_mapping_[i]: i for i in range(self.user_mapping_.shape[0])}
             self.item_dict_ = {self.item_mapping_[i]: i for i in range(self.item_mapping_.shape[0])}
         self.is_fitted = True
+        self._drop_scorer()
         del self.input_df
         del self.val_set
         return self
@@ -497,6 +523,7 @@ class HPF:
 
         self.niter += 1
         self.is_fitted = True
+        self._drop_scorer()
         return self
 
     def _extra_rows(self, n, seed, center, rate_value):
@@ -623,7 +650,9 @@ class HPF:
                     break
                 Theta_prev = self.Theta[-1].copy()
         else:
-            Theta, temp = self._user_factors(counts_df, maxiter, ncores, random_seed, stop_thr, self.keep_all_objs)
+            # drop-in parity: the reference passes cast_int(stop_thr) here (hpfrec/__init__.py:1153), i.e. 0, so this
+            # path never stops early and always runs `maxiter` iterations (unlike predict_factors, init:1047)
+            Theta, temp = self._user_factors(counts_df, maxiter, ncores, random_seed, 0.0, self.keep_all_objs)
             if self.keep_all_objs:
                 shp, rte = temp[0].reshape((1, -1)), temp[1].reshape((1, -1))
                 new_k_rte = self.a_prime / self.b_prime + (shp / rte).sum(axis=1, keepdims=True)
@@ -645,6 +674,7 @@ class HPF:
                     self.Gamma_rte = np.r_[self.Gamma_rte, rte]
                     self.k_rte = np.r_[self.k_rte, new_k_rte.astype(self.k_rte.dtype)]
                 self.nusers += 1
+        self._drop_scorer()
 
         if self.keep_data:
             new_items = counts_df["ItemId"].to_numpy(copy=False)
@@ -691,19 +721,13 @@ class HPF:
                 return np.nan
             return self.Theta[user].dot(self.Beta[item].T).reshape(-1)[0]
 
-        lp = self._loops
-        req = ["ENSUREARRAY", "C_CONTIGUOUS"]
+        sc = self._scorer()
         unknown = (user == -1) | (item == -1)
         if unknown.sum() == 0:
-            return lp.predict_arr(self.Theta, self.Beta,
-                                  np.require(user, dtype=lp.obj_ind_type, requirements=req),
-                                  np.require(item, dtype=lp.obj_ind_type, requirements=req), self.ncores)
+            return sc.predict(np.asarray(user, dtype=np.int64), np.asarray(item, dtype=np.int64))
         out = np.full(user.shape[0], np.nan, dtype=self.Theta.dtype)
         if (~unknown).sum() > 0:
-            out[~unknown] = lp.predict_arr(self.Theta, self.Beta,
-                                           np.require(user[~unknown], dtype=lp.obj_ind_type, requirements=req),
-                                           np.require(item[~unknown], dtype=lp.obj_ind_type, requirements=req),
-                                           self.ncores)
+            out[~unknown] = sc.predict(np.asarray(user[~unknown], dtype=np.int64), np.asarray(item[~unknown], dtype=np.int64))
         return out
 
     def topN(self, user, n=10, exclude_seen=True, items_pool=None):
@@ -732,15 +756,12 @@ class HPF:
         def back(rows):
             return self.item_mapping_[rows] if self.reindex else rows
 
+        sc = self._scorer()
+        seen = seen_by_user() if exclude_seen else None
         if items_pool is None:
-            neg = -(self.Theta[user].dot(self.Beta.T))
-            if not exclude_seen:
-                n = np.min([n, self.Beta.shape[0]])
-                top = np.argpartition(neg, n - 1)[:n]
-                return back(top[np.argsort(neg[top])])
-            n_ext = np.min([n + self._n_seen_by_user[user], self.Beta.shape[0]])
-            top = np.setdiff1d(np.argpartition(neg, n_ext - 1)[:n_ext], seen_by_user())
-            return back(top[np.argsort(neg[top])[:n]])
+            # all items, best first; the user's training items are masked on the device (the reference takes the
+            # n + n_seen best with argpartition and removes the seen ones with setdiff1d: the same set)
+            return back(sc.topn(user, min(n, self.Beta.shape[0]), seen=seen))
 
         items_pool = np.require(items_pool, requirements=["ENSUREARRAY"]).reshape(-1)
         pool_rows = items_pool
@@ -755,15 +776,10 @@ class HPF:
                 raise ValueError("No items to recommend.")
             if pool_rows.shape[0] == 1:
                 raise ValueError("Only 1 item to recommend.")
-        neg = -self.Theta[user].dot(self.Beta[pool_rows].T)
-        n = np.min([n, items_pool.shape[0]])
-        if not exclude_seen:
-            top = np.argpartition(neg, n - 1)[:n]
-            return items_pool[top[np.argsort(neg[top])]]
-        n_ext = np.min([n + self._n_seen_by_user[user], items_pool.shape[0]])
-        top = np.setdiff1d(pool_rows[np.argpartition(neg, n_ext - 1)[:n_ext]], seen_by_user())
-        neg = -self.Theta[user].dot(self.Beta[top].T)
-        return back(top[np.argsort(neg)[:n]])
+        n = int(np.min([n, items_pool.shape[0]]))
+        if exclude_seen:
+            pool_rows = np.unique(pool_rows)   # the reference's setdiff1d de-duplicates the pool on this path
+        return back(sc.topn(user, n, pool=pool_rows, seen=seen))
 
     def eval_llk(self, input_df, full_llk=False):
         """Poisson log-likelihood (plus constant unless full_llk) of the given triplets restricted to
@@ -771,14 +787,10 @@ class HPF:
         (reference hpfrec/__init__.py:1399-1446)."""
         assert self.is_fitted
         self._process_valset(input_df, valset=False)
-        lp = self._loops
-        req = ["ENSUREARRAY", "C_CONTIGUOUS"]
         vs = self.val_set
-        out = {'llk': lp.calc_llk(
-                   np.require(vs["Count"].to_numpy(copy=False), dtype=lp.c_real_t, requirements=req),
-                   np.require(vs["UserId"].to_numpy(copy=False), dtype=lp.obj_ind_type, requirements=req),
-                   np.require(vs["ItemId"].to_numpy(copy=False), dtype=lp.obj_ind_type, requirements=req),
-                   self.Theta, self.Beta, self.k, int(self.ncores), int(bool(full_llk))),
+        o = self._scorer().llk(vs["UserId"].to_numpy(copy=False).astype(np.int64), vs["ItemId"].to_numpy(copy=False).astype(np.int64),
+                               vs["Count"].to_numpy(copy=False), full_llk)
+        out = {'llk': np.longdouble(o[0]) - np.longdouble(o[2]),   # calc_llk, pxi:525-534
                'nobs': vs.shape[0]}
         del self.val_set
         return out

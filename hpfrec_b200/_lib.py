@@ -31,6 +31,7 @@ SIGNATURES = {
     "hpf_sweep": ([_P], _c.c_int),
     "hpf_sweep_side": ([_P, _I32], _c.c_int),
     "hpf_update_users": ([_P], _c.c_int),
+    "hpf_update_users_ex": ([_P, _c.c_int32], _c.c_int),
     "hpf_update_items": ([_P], _c.c_int),
     "hpf_partials": ([_P, _c.POINTER(_P), _c.POINTER(_I64), _c.POINTER(_P), _c.POINTER(_I64)], _c.c_int),
     "hpf_peer_export": ([_P, _P], _c.c_int),
@@ -40,9 +41,15 @@ SIGNATURES = {
     "hpf_beta_colsum": ([_P, _c.POINTER(_P), _c.POINTER(_I64)], _c.c_int),
     "hpf_step_batch": ([_P, _P, _P, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _D, _D, _I32], _c.c_int),
     "hpf_step_batch_ids": ([_P, _P, _I64, _I32, _I32, _D, _D, _I32], _c.c_int),
+    "hpf_step_epoch_ids": ([_P, _P, _I64, _I32, _I64, _I32, _D], _c.c_int),
     "hpf_llk": ([_P, _P, _P, _P, _I64, _I32, _I32, _c.POINTER(_D)], _c.c_int),
     "hpf_llk_train": ([_P, _I32, _c.POINTER(_D)], _c.c_int),
     "hpf_predict": ([_P, _P, _P, _I64, _I32, _P], _c.c_int),
+    "hpf_scorer_create": ([_c.POINTER(_P), _P, _P, _I64, _I64, _I32, _I32, _I32], _c.c_int),
+    "hpf_scorer_destroy": ([_P], _c.c_int),
+    "hpf_scorer_predict": ([_P, _P, _P, _I64, _I32, _P], _c.c_int),
+    "hpf_scorer_llk": ([_P, _P, _P, _P, _I64, _I32, _I32, _c.POINTER(_D)], _c.c_int),
+    "hpf_scorer_topn": ([_P, _I64, _I32, _P, _I64, _P, _I64, _I32, _c.POINTER(_I64), _P, _c.POINTER(_I32)], _c.c_int),
     "hpf_update_shapes": ([_I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I32, _D, _D],
                           _c.c_int),
     "hpf_digamma": ([_I32, _I32, _P, _P, _I64], _c.c_int),

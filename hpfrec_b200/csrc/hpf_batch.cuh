@@ -199,9 +199,19 @@ __global__ void __launch_bounds__(256)
 batch_minor_kernel(int nrows, const int* __restrict__ rows, int ld, int k, const real* __restrict__ x,
                    const real* __restrict__ acc, const real* __restrict__ direct, real* __restrict__ shp, real* __restrict__ rte,
                    real* __restrict__ rate, const int* __restrict__ stamp, int step,
-                   const double* __restrict__ colsum_major, real prior, real shp_rate, real add_rate,
-                   real rho, real mult, int blend_all) {
+                   const double* __restrict__ colsum_major, double* __restrict__ colsum_minor, real prior,
+                   real shp_rate, real add_rate, real rho, real mult, int blend_all) {
     constexpr int EPV = Pack<real>::N;
+    // colsum_minor += (new - old) expectation of the rows this step changes, so that the next step does not
+    // have to re-sum the whole side (double accumulation; shared memory first, one global atomic per column)
+    extern __shared__ double s_col[];
+    for (int j = threadIdx.x; j < ld; j += blockDim.x) s_col[j] = 0.0;
+    __syncthreads();
+    double dsum[VPL][EPV];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v)
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) dsum[v][e] = 0.0;
     const int gl = (threadIdx.x & 31) % LPG;
     const unsigned gmask = group_mask<LPG>();
     const int groups_per_block = blockDim.x / LPG;
@@ -239,8 +249,10 @@ batch_minor_kernel(int nrows, const int* __restrict__ rows, int ld, int k, const
 #pragma unroll
                 for (int e = 0; e < EPV; ++e) {
                     if (off[v] + e < k) {
+                        const real old_e = sv.v[e] / tv.v[e];
                         sv.v[e] = rm * (fma(xv.v[e], av.v[e], prior) + dv.v[e]) + prev * sv.v[e];
                         tv.v[e] = rho * (inv + other[v][e]) + prev * tv.v[e];
+                        dsum[v][e] += (double)(sv.v[e] / tv.v[e]) - (double)old_e;
                     }
                 }
                 st_pack(shp + (size_t)r * ld + off[v], sv);
@@ -253,6 +265,16 @@ batch_minor_kernel(int nrows, const int* __restrict__ rows, int ld, int k, const
         rowsum = group_sum<LPG>(rowsum, gmask);
         if (gl == 0) rate[r] = rho * (add_rate + rowsum) + prev * old_rate;
     }
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        if (!act[v]) continue;
+#pragma unroll
+        for (int e = 0; e < EPV; ++e)
+            if (off[v] + e < k && dsum[v][e] != 0.0) atomicAdd(&s_col[off[v] + e], dsum[v][e]);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < k; j += blockDim.x)
+        if (s_col[j] != 0.0) atomicAdd(colsum_minor + j, s_col[j]);
 }
 
 // ---------------------------------------------------------------------------------------------

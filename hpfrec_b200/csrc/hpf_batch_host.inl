@@ -64,10 +64,13 @@ int batch_core(hpf_engine* h, const int* iu, const int* ii, const void* yv, int6
         CKK();
         // 2. phi + scatter over the batch triples (update_phi + update_G_n_L_sh)
         TRY(launch_sweep_coo<C>(h, iu, ii, yv, nnz, h->xu, h->xi, h->accU, h->accI, ld, nullptr, k, h->stream));
-        // 3. column sums of the minor side's current expectation (Beta.sum(0) at pxi:300, Theta.sum(0) at 352)
-        CK(cudaMemsetAsync(csm, 0, sizeof(double) * ld, h->stream));
+        // 3. column sums of the minor side's current expectation (Beta.sum(0) at pxi:300, Theta.sum(0) at 352).
+        //    Between consecutive minibatch steps they are carried: the major kernel recomputes its side's sums in
+        //    full, the minor kernel adds the change of its batch rows (in double), so only the first step after
+        //    anything else touched the state pays the full pass.
         CK(cudaMemsetAsync(csM, 0, sizeof(double) * ld, h->stream));
-        if (nm > 0) {
+        if (!h->batch_colsums_valid) CK(cudaMemsetAsync(csm, 0, sizeof(double) * ld, h->stream));
+        if (nm > 0 && !h->batch_colsums_valid) {
             long long want = (nm * (long long)ld + 255) / 256;
             if (want > 148 * 8) want = 148 * 8;
             hpf::colsum_kernel<real><<<(unsigned)want, 256, smem, h->stream>>>(nm, ld, k, shpm, rtem, csm);
@@ -86,12 +89,13 @@ int batch_core(hpf_engine* h, const int* iu, const int* ii, const void* yv, int6
         const bool walk_all = blend_all || list_minor == nullptr;
         const int64_t nrows5 = walk_all ? nm : n_minor_ids;
         if (nrows5 > 0) {
-            hpf::batch_minor_kernel<real, C::lpg, C::vpl><<<row_grid(nrows5, C::lpg), 256, 0, h->stream>>>(
+            hpf::batch_minor_kernel<real, C::lpg, C::vpl><<<row_grid(nrows5, C::lpg), 256, smem, h->stream>>>(
                 (int)nrows5, walk_all ? nullptr : list_minor, ld, k, xm, accm, dirm, shpm, rtem, ratem, stampm, step, csM,
-                priorm, srm, addm, (real)rho, (real)mult, blend_all ? 1 : 0);
+                csm, priorm, srm, addm, (real)rho, (real)mult, blend_all ? 1 : 0);
             h->launches++;
             CKK();
         }
+        h->batch_colsums_valid = true;
         return HPF_OK;
     });
 }
@@ -259,4 +263,155 @@ extern "C" int hpf_step_batch_ids(hpf_engine* h, const void* ids, int64_t n_ids,
     const int* iu = ub ? h->bt_major : h->bt_minor;
     const int* ii = ub ? h->bt_minor : h->bt_major;
     return batch_core(h, iu, ii, h->bt_val, total, h->bt_ids, n_ids, nullptr, 0, ub, rho, mult, blend_all_rates != 0, step);
+}
+
+
+namespace {
+
+// host copies of the CSR / CSC row pointers: minibatch sizes are then known without a device round trip
+int ensure_host_ptrs(hpf_engine* h) {
+    if (!h->hA_ptr.empty() || !h->hB_ptr.empty()) return HPF_OK;
+    h->hA_ptr.resize((size_t)h->nU + 1);
+    h->hB_ptr.resize((size_t)h->nI + 1);
+    CK(cudaMemcpyAsync(h->hA_ptr.data(), h->A_ptr, sizeof(int) * ((size_t)h->nU + 1), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->hB_ptr.data(), h->B_ptr, sizeof(int) * ((size_t)h->nI + 1), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return HPF_OK;
+}
+
+}  // namespace
+
+// One whole SVI epoch (pxi:275-325 or 329-377): the shuffled id list is cut into consecutive minibatches of
+// `batch_rows` ids, multiplier n / |batch| (pxi:282 / 334), batch rows only for the hierarchical rates.  The
+// list crosses to the device once, minibatch sizes come from host copies of the row pointers, and nothing
+// in the loop waits for the device: the call returns with the epoch's kernels in flight (stream-ordered
+// with everything that follows), so the caller's shuffle of the next epoch overlaps them.
+extern "C" int hpf_step_epoch_ids(hpf_engine* h, const void* ids, int64_t n_ids, int32_t index_bytes,
+                                  int64_t batch_rows, int32_t user_batch, double rho) {
+    if (!h) return fail(HPF_EINVAL, "engine is NULL");
+    if (!h->state_loaded || !h->mat_valid) return fail(HPF_ESTATE, "no state loaded (call hpf_load_state first)");
+    if (!h->data_loaded || !h->A_ptr || !h->B_ptr)
+        return fail(HPF_ESTATE, "hpf_step_epoch_ids needs triples loaded with a single L2 panel per side "
+                                "(set option panel_mb large enough before hpf_load_coo)");
+    const bool ub = user_batch != 0;
+    const int64_t n_major = ub ? h->nU : h->nI;
+    if (n_ids < 0 || n_ids > n_major) return fail(HPF_EINVAL, "bad n_ids");
+    if (batch_rows <= 0) return fail(HPF_EINVAL, "batch_rows must be positive");
+    if (index_bytes != 4 && index_bytes != 8) return fail(HPF_EINVAL, "index_bytes must be 4 or 8");
+    if (n_ids > 0 && !ids) return fail(HPF_EINVAL, "NULL id list");
+    if (!(rho >= 0.0 && rho <= 1.0)) return fail(HPF_EINVAL, "step size must be in [0, 1]");
+    if (n_ids == 0) return HPF_OK;
+    DeviceGuard guard(h->device);
+    TRY(ensure_stamps(h));
+    TRY(ensure_host_ptrs(h));
+    // host view of the ids (range-checked here, so the device never sees a bad one) in one of two pinned
+    // staging buffers: a pageable source would make cudaMemcpyAsync wait for the stream (the previous epoch)
+    const int flip = h->ep_flip;
+    h->ep_flip ^= 1;
+    if (n_ids > h->ep_pin_cap[flip]) {
+        if (h->ep_pin[flip]) {
+            CK(cudaEventSynchronize(h->ep_ev[flip]));
+            CK(cudaFreeHost(h->ep_pin[flip]));
+            h->ep_pin[flip] = nullptr;
+        }
+        CK(cudaHostAlloc((void**)&h->ep_pin[flip], sizeof(int) * (size_t)(n_ids + n_ids / 4 + 16), cudaHostAllocDefault));
+        h->ep_pin_cap[flip] = n_ids + n_ids / 4 + 16;
+        if (!h->ep_ev[flip]) CK(cudaEventCreateWithFlags(&h->ep_ev[flip], cudaEventDisableTiming));
+    } else {
+        CK(cudaEventSynchronize(h->ep_ev[flip]));  // the copy that last used this buffer (two epochs ago) is done
+    }
+    int* hid = h->ep_pin[flip];
+    {
+        std::vector<char> tmp;
+        const void* src = ids;
+        if (is_device_ptr(ids)) {
+            tmp.resize((size_t)n_ids * index_bytes);
+            CK(cudaMemcpy(tmp.data(), ids, tmp.size(), cudaMemcpyDeviceToHost));
+            src = tmp.data();
+        }
+        for (int64_t q = 0; q < n_ids; ++q) {
+            const long long v = index_bytes == 8 ? ((const long long*)src)[q] : (long long)((const int*)src)[q];
+            if (v < 0 || v >= n_major) return fail(HPF_EINVAL, "batch id out of range");
+            hid[(size_t)q] = (int)v;
+        }
+    }
+    const std::vector<int>& hp = ub ? h->hA_ptr : h->hB_ptr;
+    const int64_t nb = (n_ids + batch_rows - 1) / batch_rows;
+    std::vector<int64_t> totals((size_t)nb, 0);
+    int64_t max_total = 0;
+    for (int64_t b = 0; b < nb; ++b) {
+        const int64_t q0 = b * batch_rows, q1 = q0 + batch_rows < n_ids ? q0 + batch_rows : n_ids;
+        int64_t t = 0;
+        for (int64_t q = q0; q < q1; ++q) t += hp[(size_t)hid[(size_t)q] + 1] - hp[(size_t)hid[(size_t)q]];
+        totals[(size_t)b] = t;
+        if (t > max_total) max_total = t;
+    }
+    // grow-only scratch; growing frees blocks that kernels of an earlier call may still use -> drain first
+    const int64_t rows_cap = batch_rows < n_ids ? batch_rows : n_ids;
+    const bool grow = n_ids > h->ep_cap_ids || !h->ep_ids || rows_cap + 1 > h->bt_cap_ids || !h->bt_cnt ||
+                      max_total > h->bt_cap_nnz || !h->bt_major;
+    if (grow) CK(cudaStreamSynchronize(h->stream));
+    if (n_ids > h->ep_cap_ids || !h->ep_ids) TRY(grow_bytes((void**)&h->ep_ids, &h->ep_cap_ids, n_ids, sizeof(int)));
+    if (rows_cap + 1 > h->bt_cap_ids || !h->bt_cnt) {
+        int64_t c1 = 0, c2 = 0, c3 = 0;
+        TRY(grow_bytes((void**)&h->bt_ids, &c1, rows_cap + 1, sizeof(int)));
+        TRY(grow_bytes((void**)&h->bt_cnt, &c2, rows_cap + 1, sizeof(int)));
+        TRY(grow_bytes((void**)&h->bt_off, &c3, rows_cap + 1, sizeof(int)));
+        h->bt_cap_ids = c1;
+    }
+    if (max_total > h->bt_cap_nnz || !h->bt_major) {
+        int64_t c1 = 0, c2 = 0, c3 = 0;
+        TRY(grow_bytes((void**)&h->bt_major, &c1, max_total, sizeof(int)));
+        TRY(grow_bytes((void**)&h->bt_minor, &c2, max_total, sizeof(int)));
+        TRY(grow_bytes(&h->bt_val, &c3, max_total, (size_t)h->rb));
+        h->bt_cap_nnz = c1;
+    }
+    size_t need = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, need, h->bt_cnt, h->bt_off, (int)rows_cap + 1, h->stream);
+    if (need > h->bt_scan_bytes) {
+        CK(cudaStreamSynchronize(h->stream));
+        hpf_free(h->bt_scan_tmp);
+        h->bt_scan_tmp = nullptr;
+        h->bt_scan_bytes = 0;
+        CK(hpf_malloc(&h->bt_scan_tmp, need + 256));
+        h->bt_scan_bytes = need + 256;
+    }
+    CK(cudaMemcpyAsync(h->ep_ids, hid, sizeof(int) * (size_t)n_ids, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaEventRecord(h->ep_ev[flip], h->stream));
+
+    const int* ptr = ub ? h->A_ptr : h->B_ptr;
+    const int* src_minor = ub ? h->A_col : h->B_col;
+    const void* src_val = ub ? h->A_val : h->B_val;
+    int* stamp_minor = ub ? h->stamp_i : h->stamp_u;
+    for (int64_t b = 0; b < nb; ++b) {
+        const int64_t q0 = b * batch_rows, q1 = q0 + batch_rows < n_ids ? q0 + batch_rows : n_ids;
+        const int64_t nq = q1 - q0, total = totals[(size_t)b];
+        const int* d_ids = h->ep_ids + q0;
+        h->batch_step += 1;
+        const int step = h->batch_step;
+        CK(cudaMemsetAsync(h->bt_cnt + nq, 0, sizeof(int), h->stream));
+        hpf::batch_count_kernel<<<nblk(nq), 256, 0, h->stream>>>((int)nq, d_ids, ptr, h->bt_cnt);
+        size_t bytes = h->bt_scan_bytes;
+        cub::DeviceScan::ExclusiveSum(h->bt_scan_tmp, bytes, h->bt_cnt, h->bt_off, (int)nq + 1, h->stream);
+        h->launches += 2;
+        if (total > 0) {
+            long long want = ((long long)nq * 32 + 255) / 256;
+            if (want > 148 * 16) want = 148 * 16;
+            if (h->rb == 4)
+                hpf::batch_expand_kernel<float><<<(unsigned)want, 256, 0, h->stream>>>(
+                    (int)nq, d_ids, ptr, h->bt_off, src_minor, (const float*)src_val, h->bt_major, h->bt_minor,
+                    (float*)h->bt_val, stamp_minor, step);
+            else
+                hpf::batch_expand_kernel<double><<<(unsigned)want, 256, 0, h->stream>>>(
+                    (int)nq, d_ids, ptr, h->bt_off, src_minor, (const double*)src_val, h->bt_major, h->bt_minor,
+                    (double*)h->bt_val, stamp_minor, step);
+            h->launches++;
+        }
+        CKK();
+        const int* iu = ub ? h->bt_major : h->bt_minor;
+        const int* ii = ub ? h->bt_minor : h->bt_major;
+        const double mult = (double)n_major / (double)nq;
+        TRY(batch_core(h, iu, ii, h->bt_val, total, d_ids, nq, nullptr, 0, ub, rho, mult, false, step));
+    }
+    return HPF_OK;
 }

@@ -87,6 +87,33 @@ int dispatch(int real_bytes, int ld, F&& f) {
                 real_bytes);
 }
 
+// Row stride: rows are padded so that every row starts on a boundary of `row_align` bytes.  32 = whole
+// sectors (smallest footprint); 128 = whole cache lines, so a lane group's 128-byte load or RED never
+// straddles two lines (fewer L1 tag look-ups and L2 requests per gathered row; measured in
+// profiles/).  Pad packs beyond kw are never read or written by the sweep.
+int row_layout(int k, int real_bytes, int* ld_out, int* kw_out) {
+    int row_align = kDefaultRowAlign;
+    if (const char* env = getenv("HPF_ROW_ALIGN")) row_align = atoi(env);
+    if (row_align != 32 && row_align != 64 && row_align != 128 && row_align != 256)
+        return fail(HPF_EINVAL, "HPF_ROW_ALIGN must be 32, 64, 128 or 256 (got %d)", row_align);
+    const int per_pack = 16 / real_bytes;
+    const int kw = (k + per_pack - 1) / per_pack * per_pack;
+    int ld = kw;
+    if ((size_t)kw * real_bytes > 32) {  // rows of one sector or less gain nothing from wider alignment
+        const int per_align = row_align / real_bytes;
+        // never pad a row to more than the next power of two of its size (a 36-byte row is not worth 128)
+        int cap = per_pack;
+        while (cap < kw) cap *= 2;
+        ld = (kw + per_align - 1) / per_align * per_align;
+        if (ld > cap) ld = cap;
+    }
+    const int per32 = 32 / real_bytes;  // at least whole 32-byte sectors
+    ld = (ld + per32 - 1) / per32 * per32;
+    *ld_out = ld;
+    *kw_out = kw;
+    return HPF_OK;
+}
+
 bool is_device_ptr(const void* p) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
@@ -218,13 +245,26 @@ struct hpf_engine {
     void* bt_scan_tmp = nullptr;
     size_t bt_scan_bytes = 0;
     int64_t bt_cap_nnz = 0, bt_cap_ids = 0;
+    int* ep_ids = nullptr;  // the id list of a whole epoch (hpf_step_epoch_ids)
+    int64_t ep_cap_ids = 0;
+    int* ep_pin[2] = {nullptr, nullptr};  // pinned staging of the id list, double-buffered
+    int64_t ep_pin_cap[2] = {0, 0};
+    cudaEvent_t ep_ev[2] = {nullptr, nullptr};
+    int ep_flip = 0;
+    std::vector<int> hA_ptr, hB_ptr;     // host copies of the row pointers (minibatch sizes without a device round trip)
+    bool batch_colsums_valid = false;    // Tsum / Bsum hold the current column sums of Theta / Beta (carried between minibatch steps)
     // options
     double panel_mb = kDefaultPanelMb;
     int chunk = kDefaultChunk;
     int sweep_mode = kDefaultSweepMode;
     int use_graph = 0;
-    int v_lpg = 0, v_block = 0;   // sweep-kernel shape overrides: lanes per row, CTA size (0 = default of the row class)
-    int v_hint = -1;              // L2 policies on the sweep's accesses (-1 default = on)
+    int v_lpg = 0, v_block = 0, v_depth = 0, v_minb = 0;  // sweep-kernel shape overrides: lanes per row, CTA size, rows in
+                                                          // flight per lane group, resident CTAs per SM (0 = default)
+    int v_hint = -1;              // L2 policies of the sweep (-1 default; see sweep_rows_kernel)
+    double keep_frac = 0.5;       // hint=1: fraction of the gathered lines loaded with evict_last
+    int v_smem_gather = -1;       // gathered rows staged in a shared-memory ring with cp.async (-1 default: when the row
+                                  // stride is the whole class width) or loaded straight into registers (0)
+    int v_prefetch = 0;           // 1: L2 prefetch of the gathered rows two batches ahead (measurement variant)
     int v_fullrow = -1;           // copy whole row strides instead of zero-filling pad packs (-1 default = off)
     int v_robust = -1;            // rescue path for underflowing normalisers: -1 auto (tiny shape priors), 0 off, 1 on
     bool robust_on = false;       // resolved from v_robust and (a, c) when a step starts
@@ -273,6 +313,8 @@ int free_data(hpf_engine* h) {
     hpf_free(h->A_ptr);
     hpf_free(h->B_ptr);
     h->A_ptr = h->B_ptr = nullptr;
+    h->hA_ptr.clear();
+    h->hB_ptr.clear();
     h->A_row = h->A_col = h->B_row = h->B_col = nullptr;
     h->A_val = h->B_val = nullptr;
     h->data_loaded = false;
@@ -502,6 +544,7 @@ int launch_rows_to_x(hpf_engine* h, int64_t nrows, const int* rows, const void* 
 
 // make xu/xi/Bsum consistent with the materialised state and zero the accumulators
 int ensure_x(hpf_engine* h) {
+    h->batch_colsums_valid = false;  // full-batch work owns Tsum / Bsum from here on
     if (h->x_valid) return HPF_OK;
     if (!h->state_loaded) return fail(HPF_ESTATE, "no state loaded (call hpf_load_state first)");
     CK(cudaMemsetAsync(h->Bsum, 0, sizeof(double) * h->ld, h->stream));
@@ -654,27 +697,8 @@ int hpf_create(hpf_engine** out, int64_t nU, int64_t nI, int32_t k, int32_t real
     }
     if (device < 0 || device >= ndev) return fail(HPF_EINVAL, "device %d out of range (%d devices)", device, ndev);
     DeviceGuard guard(device);
-    // Row stride: rows are padded so that every row starts on a boundary of `row_align` bytes.  32 = whole
-    // sectors (smallest footprint); 128 = whole cache lines, so a lane group's 128-byte load or RED never
-    // straddles two lines (fewer L1 tag look-ups and L2 requests per gathered row; measured in
-    // profiles/).  Pad packs beyond kw are never read or written by the sweep.
-    int row_align = kDefaultRowAlign;
-    if (const char* env = getenv("HPF_ROW_ALIGN")) row_align = atoi(env);
-    if (row_align != 32 && row_align != 64 && row_align != 128 && row_align != 256)
-        return fail(HPF_EINVAL, "HPF_ROW_ALIGN must be 32, 64, 128 or 256 (got %d)", row_align);
-    const int per_pack = 16 / real_bytes;
-    const int kw = (k + per_pack - 1) / per_pack * per_pack;
-    int ld = kw;
-    if ((size_t)kw * real_bytes > 32) {  // rows of one sector or less gain nothing from wider alignment
-        const int per_align = row_align / real_bytes;
-        // never pad a row to more than the next power of two of its size (a 36-byte row is not worth 128)
-        int cap = per_pack;
-        while (cap < kw) cap *= 2;
-        ld = (kw + per_align - 1) / per_align * per_align;
-        if (ld > cap) ld = cap;
-    }
-    const int per32 = 32 / real_bytes;  // at least whole 32-byte sectors
-    ld = (ld + per32 - 1) / per32 * per32;
+    int ld = 0, kw = 0;
+    TRY(row_layout(k, real_bytes, &ld, &kw));
     TRY(dispatch(real_bytes, ld, [](auto) { return HPF_OK; }));
     hpf_engine* h = new hpf_engine();
     h->device = device;
@@ -749,8 +773,12 @@ int hpf_destroy(hpf_engine* h) {
         if (e) cudaEventDestroy(e);
     for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
     h->ipc_opened.clear();
+    for (int b = 0; b < 2; ++b) {
+        if (h->ep_pin[b]) cudaFreeHost(h->ep_pin[b]);
+        if (h->ep_ev[b]) cudaEventDestroy(h->ep_ev[b]);
+    }
     void* ptrs[] = {h->Gshp, h->Grte, h->Lshp, h->Lrte, h->krte, h->trte, h->xu, h->xi, h->accU, h->accI, h->Tsum, h->Bsum, h->stamp_u, h->stamp_i,
-                    h->bt_major, h->bt_minor, h->bt_cnt, h->bt_off, h->bt_ids, h->bt_val, h->bt_scan_tmp, h->dirU, h->dirI};
+                    h->bt_major, h->bt_minor, h->bt_cnt, h->bt_off, h->bt_ids, h->bt_val, h->bt_scan_tmp, h->dirU, h->dirI, h->ep_ids};
     for (void* p : ptrs) hpf_free(p);
     delete h;
     return HPF_OK;
@@ -814,14 +842,30 @@ int hpf_set_option(hpf_engine* h, const char* name, double value) {
         if (value != 0 && value != 1) return fail(HPF_EINVAL, "sweep must be 0 (two-pass) or 1 (single-pass COO cross-check)");
         h->sweep_mode = (int)value;
         drop_graphs(h);
-    } else if (!strcmp(name, "lpg") || !strcmp(name, "block")) {
+    } else if (!strcmp(name, "lpg") || !strcmp(name, "block") || !strcmp(name, "depth") || !strcmp(name, "minb")) {
         if (value < 0 || value > 1024) return fail(HPF_EINVAL, "%s out of range", name);
         if (!strcmp(name, "lpg")) h->v_lpg = (int)value;      // 0 = default of the row class
         if (!strcmp(name, "block")) h->v_block = (int)value;  // 0 = default
+        if (!strcmp(name, "depth")) h->v_depth = (int)value;  // 0 = default
+        if (!strcmp(name, "minb")) h->v_minb = (int)value;    // 0 = default
         drop_graphs(h);
-    } else if (!strcmp(name, "hint") || !strcmp(name, "fullrow") || !strcmp(name, "robust")) {
+    } else if (!strcmp(name, "keep_frac")) {
+        if (!(value >= 0.0 && value <= 1.0)) return fail(HPF_EINVAL, "keep_frac must be in [0, 1]");
+        h->keep_frac = value;
+        drop_graphs(h);
+    } else if (!strcmp(name, "hint")) {
+        if (value != -1 && value != 0 && value != 1 && value != 2) return fail(HPF_EINVAL, "hint must be -1 (default), 0, 1 or 2");
+        h->v_hint = (int)value;
+        drop_graphs(h);
+    } else if (!strcmp(name, "smem_gather")) {
+        if (value != -1 && value != 0 && value != 1) return fail(HPF_EINVAL, "smem_gather must be -1 (default), 0 or 1");
+        h->v_smem_gather = (int)value;
+        drop_graphs(h);
+    } else if (!strcmp(name, "prefetch")) {
+        h->v_prefetch = value > 0 ? (int)value : 0;
+        drop_graphs(h);
+    } else if (!strcmp(name, "fullrow") || !strcmp(name, "robust")) {
         if (value != -1 && value != 0 && value != 1) return fail(HPF_EINVAL, "%s must be -1 (default), 0 or 1", name);
-        if (!strcmp(name, "hint")) h->v_hint = (int)value;
         if (!strcmp(name, "fullrow")) h->v_fullrow = (int)value;
         if (!strcmp(name, "robust")) h->v_robust = (int)value;
         drop_graphs(h);
@@ -864,6 +908,7 @@ int hpf_load_state(hpf_engine* h, const void* Gamma_shp, const void* Gamma_rte, 
     h->state_loaded = true;
     h->mat_valid = true;
     h->x_valid = false;
+    h->batch_colsums_valid = false;
     return HPF_OK;
 }
 
@@ -982,11 +1027,13 @@ int hpf_sweep_side(hpf_engine* h, int32_t side) {
     return do_sweep(h, side == 0 ? 1 : 2);
 }
 
-int hpf_update_users(hpf_engine* h) {
+int hpf_update_users(hpf_engine* h) { return hpf_update_users_ex(h, 1); }
+
+int hpf_update_users_ex(hpf_engine* h, int32_t materialize) {
     if (!h) return fail(HPF_EINVAL, "engine is NULL");
     if (!h->x_valid) return fail(HPF_ESTATE, "hpf_update_users must follow hpf_sweep");
     DeviceGuard guard(h->device);
-    return do_update(h, true, true);
+    return do_update(h, true, materialize != 0);
 }
 
 int hpf_update_items(hpf_engine* h) {
@@ -1158,21 +1205,26 @@ int hpf_describe(hpf_engine* h, char* buf, int64_t n) {
     const int packs_row = h->ld * h->rb / 16;
     int cls = 8;
     while (cls < packs_row) cls *= 2;
-    const RowsShape d = default_rows_shape(cls, h->rb);
-    int lpg = h->v_lpg ? h->v_lpg : d.lpg, block = h->v_block ? h->v_block : d.block;
-    if (lpg == 0) {  // generic shape: the row class's lane-group width, 128-thread CTAs
-        lpg = cls <= 16 ? 8 : (cls <= 32 ? 16 : 32);
-        block = 128;
-    }
-    const int hint = h->v_hint >= 0 ? h->v_hint : 1;
-    const int fullrow = (h->v_fullrow > 0 && h->ld * h->rb / 16 == cls) ? 1 : 0;
     const double lo = h->a < h->c ? h->a : h->c;
     const int robust = h->v_robust >= 0 ? h->v_robust : (lo < (h->rb == 4 ? 0.05 : 0.004) ? 1 : 0);
+    const bool full_ok = h->ld * h->rb / 16 == cls;
+    const int smem_gather = h->v_smem_gather >= 0 ? h->v_smem_gather : ((full_ok && !robust) ? 1 : 0);
+    const int fullrow = full_ok ? (h->v_fullrow >= 0 ? h->v_fullrow : smem_gather) : 0;
+    const RowsShape d = default_rows_shape(cls, h->rb, smem_gather != 0);
+    int lpg = h->v_lpg ? h->v_lpg : d.lpg, block = h->v_block ? h->v_block : d.block;
+    int depth = h->v_depth ? h->v_depth : d.depth, minb = h->v_minb ? h->v_minb : d.minb;
+    if (lpg == 0) {  // generic shape: the row class's lane-group width, 128-thread CTAs, 2 rows in flight
+        lpg = cls <= 16 ? 8 : (cls <= 32 ? 16 : 32);
+        block = 128;
+        depth = 2;
+        minb = 2;
+    }
+    const int hint = h->v_hint >= 0 ? h->v_hint : kDefaultHint;
     snprintf(buf, (size_t)n,
-             "real_bytes=%d k=%d kw=%d ld=%d sweep=%d kernel=%s lpg=%d block=%d hint=%d fullrow=%d robust=%d chunk=%d "
+             "real_bytes=%d k=%d kw=%d ld=%d sweep=%d kernel=%s lpg=%d depth=%d block=%d minb=%d smem_gather=%d hint=%d fullrow=%d robust=%d chunk=%d "
              "panel_mb=%g panels_user_major=%d panels_item_major=%d launches_per_iteration=%d",
              h->rb, h->k, h->kw, h->ld, h->sweep_mode, h->sweep_mode == 1 ? "sweep_coo_kernel" : "sweep_rows_kernel", lpg,
-             block, hint, fullrow, robust, h->chunk, h->panel_mb, h->panelsA, h->panelsB, h->sweep_mode == 0 ? 4 : 3);
+             depth, block, minb, smem_gather, hint, fullrow, robust, h->chunk, h->panel_mb, h->panelsA, h->panelsB, h->sweep_mode == 0 ? 4 : 3);
     return HPF_OK;
 }
 
@@ -1395,3 +1447,4 @@ int hpf_digamma(int32_t real_bytes, int32_t device, const void* x, void* out, in
 }  // extern "C"
 
 #include "hpf_batch_host.inl"
+#include "hpf_scorer.inl"

@@ -157,15 +157,17 @@ __device__ __noinline__ void sweep_rescue(const RescueArgs<real>& ra, int r_own,
     }
 }
 
-// shared memory of one warp: gather ring, own-row ring (DEPTH slots of VPL x 512 B each), two batches of
-// staged triples (32 x 16 B each)
-template <int VPL>
+// shared memory of one warp: own-row ring (OWN_DEPTH slots of VPL x 512 B) and two batches of staged triples
+// (32 x 16 B each).  The GATHERED rows never touch shared memory: they are loaded straight into registers.
+// GD = slots of the optional gathered-row ring (0: the gathered rows go straight into registers).
+template <int VPL, int GD = 0>
 struct SweepSmem {
-    static constexpr int DEPTH = 4;
+    static constexpr int OWN_DEPTH = GD > 4 ? GD : 4;  // an own row may be staged as far ahead as a gathered one
     static constexpr uint32_t SLOT = VPL * 512u;
-    static constexpr uint32_t RING = DEPTH * SLOT;
+    static constexpr uint32_t RING = OWN_DEPTH * SLOT;
+    static constexpr uint32_t GRING = GD * SLOT;
     static constexpr uint32_t TRIP = 2u * 512u;
-    static constexpr uint32_t WARP = 2u * RING + TRIP;
+    static constexpr uint32_t WARP = RING + GRING + TRIP;
 };
 
 // staged triple, 16 bytes: float {row, col, y, row}; double {row, col, y}
@@ -184,27 +186,58 @@ __device__ __forceinline__ void lds_row_y(uint32_t addr, int& r, float& y) {
     y = __int_as_float(yb);
 }
 __device__ __forceinline__ void lds_row_y(uint32_t addr, int& r, double& y) {
-    int c, lo, hi;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r), "=r"(c), "=r"(lo), "=r"(hi) : "r"(addr));
+    int lo, hi;
+    asm volatile("{\n\t.reg .b32 c;\n\tld.shared.v4.b32 {%0, c, %1, %2}, [%3];\n\t}" : "=r"(r), "=r"(lo), "=r"(hi) : "r"(addr));
     y = __longlong_as_double(((long long)hi << 32) | (unsigned)lo);
+}
+
+// Own-row staging, deliberately NOT inlined: inlined, ptxas if-converts the rare "row id changed" block into
+// predicated LDGSTS instructions that are issued at EVERY step -- and a predicated-off LDGSTS still costs
+// shared-memory wavefronts in the L1TEX data pipe (ncu source page of the inlined form: 2 LDGSTS + 3 filler LDS
+// per step, 164 M wavefronts per launch, more than all real shared-memory traffic together).  A call is a
+// real branch.  act_mask: bit v set = pack v of this lane is inside the row's active width (else zero-fill).
+template <int LPG, int VPL, int HINT>
+__device__ __noinline__ void stage_own_row(uint32_t dst, const char* src, uint32_t act_mask, uint64_t pol) {
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        const uint32_t szv = (act_mask >> v) & 1u ? 16u : 0u;
+        if (HINT) cp_async16_sz_pol(dst + (uint32_t)v * 512u, src + v * (LPG * 16), szv, pol);
+        else cp_async16_sz(dst + (uint32_t)v * 512u, src + v * (LPG * 16), szv);
+    }
 }
 
 // =============================================================================================
 // ngroups: number of lane groups of the launch = padded nnz / chunk, a multiple of 32 / LPG.
 // chunk:   nnz per lane group, a multiple of LPG.  row/col/val hold ngroups * chunk entries.
+// D:       gathered rows in flight per lane group (register pipeline depth; divides LPG, <= 4).
+// HINT:    0 no L2 policies; 1 streamed data (triples, own rows, REDs) evict_first + gathered rows evict_last
+//          for a fraction `keep_frac` of the lines; 2 streamed data evict_first only.
+//
+// Why registers and not shared memory for the gathered rows: ncu on the shared-memory-staged revision of
+// this kernel (profiles/r02_ncu_full_smem_staged_lpg8.csv) shows the L1TEX data pipe at 89 % with 6.2
+// shared-memory wavefronts per nnz -- every gathered byte crossed shared memory twice (LDGSTS in, LDS out)
+// and the 128 B/clk/SM port was the bound (1.16-1.30 ms per pass whatever the shape, L2 panel or hint).
+// The bare staging pattern tops out at 60 G rows/s with LDGSTS and 46 G rows/s with TMA tile::gather4
+// (tools/tma_gather_probe.cu, profiles/r02_tma_gather4_probe.jsonl), against 80 G rows/s for plain
+// 128-bit loads into registers (tools/gather_probe.cu).
 // =============================================================================================
-template <typename real, int LPG, int VPL, int MINB, int BLOCK, int HINT, bool FULLROW, bool ROBUST>
+// PF:      1 = every lane asks L2 for the gathered row of its own triple two batches ahead (prefetch.global.L2):
+//          a gather that would miss L2 becomes a hit by the time it is issued; 2 = the same into L1.
+// SG:      1 = the gathered rows are staged in a shared-memory ring of D slots with cp.async (LDGSTS: no registers
+//          and no scoreboard per row in flight, but every gathered byte then crosses shared memory twice);
+//          0 = 128-bit loads straight into registers.
+template <typename real, int LPG, int VPL, int D, int MINB, int BLOCK, int HINT, bool FULLROW, bool ROBUST, int PF = 0, int SG = 0>
 __global__ void __launch_bounds__(BLOCK, MINB)
 sweep_rows_kernel(const int* __restrict__ row, const int* __restrict__ col, const real* __restrict__ val,
                   long long ngroups, int chunk, const real* __restrict__ xown, const real* __restrict__ xgat,
-                  real* __restrict__ acc, int ld, int kw, RescueArgs<real> rescue) {
+                  real* __restrict__ acc, int ld, int kw, float keep_frac, RescueArgs<real> rescue) {
     constexpr int EPV = Pack<real>::N;
     constexpr int NG = 32 / LPG;  // lane groups per warp
-    using SM = SweepSmem<VPL>;
-    constexpr int DEPTH = SM::DEPTH, LOOK = DEPTH - 1;
-    static_assert(LPG % DEPTH == 0, "lane-group width must be a multiple of the ring depth");
+    using SM = SweepSmem<VPL, SG ? D : 0>;
+    constexpr int OD = SM::OWN_DEPTH;
+    static_assert(LPG % D == 0 && LPG % OD == 0 && (SG || D <= OD), "pipeline depth must divide the lane-group width");
     constexpr unsigned FULL = 0xffffffffu;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gl = lane % LPG, g = lane / LPG;
     const long long wg0 = ((long long)blockIdx.x * (BLOCK / 32) + warp) * NG;
@@ -213,25 +246,37 @@ sweep_rows_kernel(const int* __restrict__ row, const int* __restrict__ col, cons
     const int nbatch = chunk / LPG;
 
     uint64_t pol_keep = 0, pol_stream = 0;
-    if (HINT) {
-        pol_keep = l2_policy_keep();
-        pol_stream = l2_policy_stream();
-    }
+    if (HINT) pol_stream = l2_policy_stream();
+    if (HINT == 1) asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_unchanged.b64 %0, %1;" : "=l"(pol_keep) : "f"(keep_frac));
     const unsigned row_bytes = (unsigned)ld * (unsigned)sizeof(real);
     const uint32_t wbase = smem_u32(smem_raw) + (uint32_t)warp * SM::WARP;
-    const uint32_t ring_g = wbase + (uint32_t)lane * 16u;
-    const uint32_t ring_o = ring_g + SM::RING;
-    const uint32_t trip0 = wbase + 2u * SM::RING + (uint32_t)g * 16u;  // + buffer*512 + t*NG*16
-    const unsigned off0 = (unsigned)(gl * EPV) * (unsigned)sizeof(real);
-    const char* gat_lane = reinterpret_cast<const char*>(xgat) + off0;
-    const char* own_lane = reinterpret_cast<const char*>(xown) + off0;
-    // src-size of each pack's copy: 16, or 0 (zero-fill) beyond the active width
-    uint32_t sz[VPL];
+    const uint32_t ring_o = wbase + (uint32_t)lane * 16u;
+    const uint32_t ring_g = ring_o + SM::RING;
+    // staged triples: group g's batch is LPG consecutive 16-byte slots; step t sits at slot t ^ swz so that the
+    // lanes of a quarter-warp store to 128 contiguous bytes and the broadcast reads of the NG groups at one step
+    // hit different banks (the un-swizzled [t][g] layout cost 16 wavefronts per STS.128)
+    constexpr int SWZ_MASK = (LPG >= 8 ? 7 : LPG - 1);
+    const uint32_t swz = (uint32_t)((LPG >= 8 ? g : (g >> 1)) & SWZ_MASK);
+    // the group's region is aligned to its size, so base + ((t ^ swz) * 16) == (base ^ swz * 16) ^ (t * 16): one LOP3
+    const uint32_t trip0 = (wbase + SM::RING + SM::GRING + (uint32_t)(g * LPG) * 16u) ^ (swz * 16u);  // + buffer*512, ^ (t * 16)
+    // Packs beyond the row's active width: the lane re-reads the row's LAST active pack instead (same
+    // 32-byte sector as its neighbour: no extra traffic, no predicate); its own-row registers are zero, so
+    // the duplicate never reaches the normaliser, and its sums are never flushed.
+    const int last_pack = (kw - 1) / EPV;
     bool act[VPL];
+    uint32_t act_mask = 0;
+    const char* gat_lane[VPL];
+    const char* own_lane = reinterpret_cast<const char*>(xown) + (unsigned)(gl * EPV) * (unsigned)sizeof(real);
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
-        act[v] = (gl + LPG * v) * EPV < kw;
-        sz[v] = (FULLROW || act[v]) ? 16u : 0u;
+        const int p = gl + LPG * v;
+        act[v] = p <= last_pack;
+        act_mask |= act[v] ? (1u << v) : 0u;
+        const int pc = (FULLROW || act[v]) ? p : last_pack;
+        gat_lane[v] = reinterpret_cast<const char*>(xgat) + (unsigned)pc * 16u;
+        // opaque to the optimiser: keeps the lane's base as ONE 64-bit register pair, so a row address is a single
+        // IMAD.WIDE (col * row_bytes + base) instead of a 32-bit offset chain plus a 64-bit add of the uniform base
+        asm volatile("" : "+l"(gat_lane[v]));
     }
 
     auto load_triple = [&](int b, int& r, int& c, real& y) {
@@ -246,26 +291,31 @@ sweep_rows_kernel(const int* __restrict__ row, const int* __restrict__ col, cons
             y = __ldg(val + idx);
         }
     };
-    auto copy_row = [&](uint32_t dst, const char* src, uint64_t pol) {
-#pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-            if (FULLROW) {
-                if (HINT) cp_async16_pol(dst + (uint32_t)v * 512u, src + v * (LPG * 16), pol);
-                else cp_async16(dst + (uint32_t)v * 512u, src + v * (LPG * 16));
-            } else {
-                if (HINT) cp_async16_sz_pol(dst + (uint32_t)v * 512u, src + v * (LPG * 16), sz[v], pol);
-                else cp_async16_sz(dst + (uint32_t)v * 512u, src + v * (LPG * 16), sz[v]);
-            }
-        }
-    };
+    Pack<real> gq[SG ? 1 : D][VPL];  // gathered rows in flight (register form)
     int r_staged = -1;
-    // stage one step: the gathered row always, the own row when the row id changes at that step
-    auto stage = [&](int slot, uint32_t trip_addr) {
+    // put one step in flight: its gathered row into registers, its own row (when the row id changes at
+    // that step) into the shared-memory ring
+    auto stage = [&](int s, uint32_t trip_addr) {
         int ra, ca;
         lds64(trip_addr, ra, ca);
-        copy_row(ring_g + (uint32_t)slot * SM::SLOT, gat_lane + (uint64_t)(unsigned)ca * row_bytes, pol_keep);
+        const uint64_t roff = (uint64_t)(unsigned)ca * row_bytes;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const char* srcb = (FULLROW ? gat_lane[0] + v * (LPG * 16) : gat_lane[v]) + roff;
+            if (SG) {
+                // inactive lanes re-copy the row's last active pack (see gat_lane): no predicate, no zero-fill
+                const uint32_t dst = ring_g + (uint32_t)(s % D) * SM::SLOT + (uint32_t)v * 512u;
+                if (HINT == 1) cp_async16_pol(dst, srcb, pol_keep);
+                else cp_async16(dst, srcb);
+            } else {
+                const real* src = reinterpret_cast<const real*>(srcb);
+                if (HINT == 1) gq[SG ? 0 : s % D][v] = ldg_pack_hint(src, pol_keep);
+                else gq[SG ? 0 : s % D][v] = ldg_pack(src);
+            }
+        }
         if (ra != r_staged) {
-            copy_row(ring_o + (uint32_t)slot * SM::SLOT, own_lane + (uint64_t)(unsigned)ra * row_bytes, pol_stream);
+            stage_own_row<LPG, VPL, HINT>(ring_o + (uint32_t)(s % OD) * SM::SLOT, own_lane + (uint64_t)(unsigned)ra * row_bytes,
+                                          act_mask, pol_stream);
             r_staged = ra;
         }
         cp_async_commit();
@@ -288,55 +338,65 @@ sweep_rows_kernel(const int* __restrict__ row, const int* __restrict__ col, cons
             }
     };
 
-    // ---- prologue: batches 0 and 1 into the two triple buffers, first LOOK steps staged ------------
+    // ---- prologue: batches 0 and 1 into the two triple buffers, first D steps in flight ------------
     {
         int r, c;
         real y;
         load_triple(0, r, c, y);
-        sts_triple(trip0 + (uint32_t)gl * (NG * 16u), r, c, y);
+        sts_triple(trip0 ^ ((uint32_t)gl * 16u), r, c, y);
         load_triple(nbatch > 1 ? 1 : 0, r, c, y);
-        sts_triple(trip0 + 512u + (uint32_t)gl * (NG * 16u), r, c, y);
+        sts_triple((trip0 + 512u) ^ ((uint32_t)gl * 16u), r, c, y);
     }
     __syncwarp();
 #pragma unroll
-    for (int t = 0; t < LOOK; ++t) stage(t, trip0 + (uint32_t)t * (NG * 16u));
+    for (int t = 0; t < D; ++t) stage(t, trip0 ^ ((uint32_t)t * 16u));
 
     uint32_t tb_cur = trip0, tb_nxt = trip0 + 512u;
     for (int b = 0; b < nbatch; ++b) {
-        // triples of batch b+2 (clamped: the tail re-reads the last batch, whose staging is never consumed)
+        // triples of batch b+2 (clamped: the tail re-reads the last batch; those steps are never consumed)
         int r2, c2;
         real y2;
         load_triple(b + 2 < nbatch ? b + 2 : nbatch - 1, r2, c2, y2);
+        if (PF) {
+            const char* pf = reinterpret_cast<const char*>(xgat) + (uint64_t)(unsigned)c2 * row_bytes;
+            if (PF == 2) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + 128));
+            } else {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + 128));
+            }
+        }
 #pragma unroll
         for (int t = 0; t < LPG; ++t) {
-            // ---- stage step t + LOOK (this batch or the next one)
-            if (t + LOOK < LPG) stage((t + LOOK) % DEPTH, tb_cur + (uint32_t)(t + LOOK) * (NG * 16u));
-            else stage((t + LOOK) % DEPTH, tb_nxt + (uint32_t)(t + LOOK - LPG) * (NG * 16u));
-            cp_async_wait<LOOK>();  // all but the newest LOOK groups have landed: step t is in
             // ---- consume step t
             int rr;
             real yy;
-            lds_row_y(tb_cur + (uint32_t)t * (NG * 16u), rr, yy);
-            const uint32_t slot_off = (uint32_t)(t % DEPTH) * SM::SLOT;
+            lds_row_y(tb_cur ^ ((uint32_t)t * 16u), rr, yy);
+            if (SG) cp_async_wait<D - 1>();  // all but the newest D-1 groups have landed: step t is in
             if (rr != cur) {  // divergent between groups, no shuffles inside
                 if (cur >= 0) flush();
                 cur = rr;
+                if (!SG) cp_async_wait<D - 1>();  // own rows of all steps up to t have landed
 #pragma unroll
                 for (int v = 0; v < VPL; ++v) {
-                    own[v] = lds_pack<real>(ring_o + slot_off + (uint32_t)v * 512u);
+                    own[v] = lds_pack<real>(ring_o + (uint32_t)(t % OD) * SM::SLOT + (uint32_t)v * 512u);
                     sum[v] = pack_zero<real>();
                 }
             }
             Pack<real> gv[VPL];
 #pragma unroll
-            for (int v = 0; v < VPL; ++v) gv[v] = lds_pack<real>(ring_g + slot_off + (uint32_t)v * 512u);
+            for (int v = 0; v < VPL; ++v) {
+                if (SG) gv[v] = lds_pack<real>(ring_g + (uint32_t)(t % D) * SM::SLOT + (uint32_t)v * 512u);
+                else gv[v] = gq[SG ? 0 : t % D][v];
+            }
             typename DotOf<real>::type d0, d1;
 #pragma unroll
             for (int v = 0; v < VPL; ++v) {
-                if (v & 1) d1.add(own[v], gv[v]);
+                if ((v & 1) && VPL > 2) d1.add(own[v], gv[v]);
                 else d0.add(own[v], gv[v]);
             }
-            real s = VPL > 1 ? d0.total() + d1.total() : d0.total();
+            real s = VPL > 2 ? d0.total() + d1.total() : d0.total();
 #pragma unroll
             for (int o = LPG / 2; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o, LPG);
             real w = rdiv_rcp(yy, s);
@@ -344,7 +404,7 @@ sweep_rows_kernel(const int* __restrict__ row, const int* __restrict__ col, cons
                 if (!(s >= rescue_threshold<real>())) {  // group-uniform (s is the group's sum)
                     if (yy > real(0)) {
                         int ra_, ca_;
-                        lds64(tb_cur + (uint32_t)t * (NG * 16u), ra_, ca_);
+                        lds64(tb_cur ^ ((uint32_t)t * 16u), ra_, ca_);
                         sweep_rescue<real, LPG, VPL>(rescue, cur, ca_, yy, ld, gl);
                     }
                     w = real(0);
@@ -352,10 +412,13 @@ sweep_rows_kernel(const int* __restrict__ row, const int* __restrict__ col, cons
             }
 #pragma unroll
             for (int v = 0; v < VPL; ++v) axpy_pack(sum[v], w, gv[v]);
+            // ---- put step t + D in flight (this batch or the next one), into the registers just consumed
+            if (t + D < LPG) stage(t + D, tb_cur ^ ((uint32_t)(t + D) * 16u));
+            else stage(t + D, tb_nxt ^ ((uint32_t)(t + D - LPG) * 16u));
         }
         // batch b is consumed: its buffer takes batch b+2
         __syncwarp();
-        sts_triple(tb_cur + (uint32_t)gl * (NG * 16u), r2, c2, y2);
+        sts_triple(tb_cur ^ ((uint32_t)gl * 16u), r2, c2, y2);
         __syncwarp();
         const uint32_t tmp = tb_cur;
         tb_cur = tb_nxt;

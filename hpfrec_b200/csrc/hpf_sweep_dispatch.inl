@@ -12,11 +12,12 @@ inline long long padded_groups(int64_t nnz, int chunk, int lpg) {
     return (groups + per_warp - 1) / per_warp * per_warp;
 }
 
-template <typename real, int LPG, int VPL, int MINB, int BLOCK, int HINT, bool FULLROW, bool ROBUST>
+template <typename real, int LPG, int VPL, int D, int MINB, int BLOCK, int HINT, bool FULLROW, bool ROBUST, int PF = 0, int SG = 0>
 int launch_sweep_rows(hpf_engine* h, const int* row, const int* col, const void* val, const void* xown,
                       const void* xgat, void* acc, const hpf::RescueArgs<real>& rescue) {
-    auto kern = hpf::sweep_rows_kernel<real, LPG, VPL, MINB, BLOCK, HINT, FULLROW, ROBUST>;
-    constexpr int smem = (BLOCK / 32) * (int)hpf::SweepSmem<VPL>::WARP;
+    auto kern = hpf::sweep_rows_kernel<real, LPG, VPL, D, MINB, BLOCK, HINT, FULLROW, ROBUST, PF, SG>;
+    constexpr int smem = (BLOCK / 32) * (int)hpf::SweepSmem<VPL, SG ? D : 0>::WARP;
+    static_assert(smem <= 227 * 1024, "shape does not fit shared memory");
     static thread_local bool configured[64] = {};  // the attribute is per device
     if (h->device >= 64 || !configured[h->device]) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -26,49 +27,64 @@ int launch_sweep_rows(hpf_engine* h, const int* row, const int* col, const void*
     const long long warps = groups / (32 / LPG);
     const unsigned grid = (unsigned)((warps + BLOCK / 32 - 1) / (BLOCK / 32));
     kern<<<grid, BLOCK, smem, h->stream>>>(row, col, (const real*)val, groups, h->chunk, (const real*)xown,
-                                           (const real*)xgat, (real*)acc, h->ld, h->kw, rescue);
+                                           (const real*)xgat, (real*)acc, h->ld, h->kw, (float)h->keep_frac, rescue);
     h->launches++;
     CKK();
     return HPF_OK;
 }
 
-// run-time flags -> template flags.  The hint-less and FULLROW forms are measurement variants, compiled for the
-// headline row class only (TUNE); ROBUST is built with the default hints and without FULLROW.
-template <typename real, int LPG, int VPL, int MINB, int BLOCK, bool TUNE>
+// run-time flags -> template flags.  Two production forms per shape: the shared-memory ring with whole-stride
+// copies (SG + FULLROW: the measured best, needs the row stride to be the whole class width) and the register
+// form (any stride; also what ROBUST is built on).  The other combinations are measurement variants, compiled
+// for the headline row class only (TUNE).
+constexpr int kDefaultHint = 0;   // L2 policies measured neutral-to-harmful (profiles/r02_tune_*.jsonl, traffic probe)
+template <typename real, int LPG, int VPL, int D, int MINB, int BLOCK, bool TUNE>
 int launch_sweep_rows_flags(hpf_engine* h, const int* row, const int* col, const void* val, const void* xown,
                             const void* xgat, void* acc, const hpf::RescueArgs<real>& rescue, int hint, bool fullrow,
-                            bool robust) {
-    if (robust) return launch_sweep_rows<real, LPG, VPL, MINB, BLOCK, 1, false, true>(h, row, col, val, xown, xgat, acc, rescue);
-    if constexpr (TUNE) {
-        if (fullrow) {
-            if (hint) return launch_sweep_rows<real, LPG, VPL, MINB, BLOCK, 1, true, false>(h, row, col, val, xown, xgat, acc, rescue);
-            return launch_sweep_rows<real, LPG, VPL, MINB, BLOCK, 0, true, false>(h, row, col, val, xown, xgat, acc, rescue);
+                            bool smem_gather, bool robust) {
+    if (smem_gather && !robust) {
+        if (fullrow && hint == 0) return launch_sweep_rows<real, LPG, VPL, D, MINB, BLOCK, 0, true, false, 0, 1>(h, row, col, val, xown, xgat, acc, rescue);
+        if constexpr (TUNE) {
+            if (fullrow) return launch_sweep_rows<real, LPG, VPL, D, MINB, BLOCK, 2, true, false, 0, 1>(h, row, col, val, xown, xgat, acc, rescue);
+            return launch_sweep_rows<real, LPG, VPL, D, MINB, BLOCK, 0, false, false, 0, 1>(h, row, col, val, xown, xgat, acc, rescue);
+        } else if (h->strict) {
+            return fail(HPF_EINVAL, "this smem_gather / fullrow / hint combination is only built for the k<=64 fp32 row class");
         }
-        if (!hint) return launch_sweep_rows<real, LPG, VPL, MINB, BLOCK, 0, false, false>(h, row, col, val, xown, xgat, acc, rescue);
-    } else if (h->strict && (fullrow || !hint)) {
-        return fail(HPF_EINVAL, "hint=0 / fullrow=1 are only built for the k<=64 fp32 row class");
+        if (fullrow) return launch_sweep_rows<real, LPG, VPL, D, MINB, BLOCK, 0, true, false, 0, 1>(h, row, col, val, xown, xgat, acc, rescue);
     }
-    return launch_sweep_rows<real, LPG, VPL, MINB, BLOCK, 1, false, false>(h, row, col, val, xown, xgat, acc, rescue);
-}
-
-// resident CTAs per SM that the shared-memory footprint of a shape allows (also its launch bound)
-template <int VPL, int BLOCK>
-constexpr int smem_ctas() {
-    constexpr int per_cta = (BLOCK / 32) * (int)hpf::SweepSmem<VPL>::WARP + 1024;
-    constexpr int fit = (227 * 1024) / per_cta;
-    constexpr int by_threads = 2048 / BLOCK;
-    return fit < 1 ? 1 : (fit > by_threads ? by_threads : (fit > 8 ? 8 : fit));
+    if constexpr (D > 4) {
+        return fail(HPF_EINVAL, "more than 4 rows in flight per lane group need the shared-memory ring (smem_gather=1, full row stride)");
+    } else {
+        if (robust) return launch_sweep_rows<real, LPG, VPL, D, MINB, BLOCK, 0, false, true>(h, row, col, val, xown, xgat, acc, rescue);
+        if constexpr (TUNE) {
+            if (h->v_prefetch == 1 && !fullrow) return launch_sweep_rows<real, LPG, VPL, D, MINB, BLOCK, 0, false, false, 1>(h, row, col, val, xown, xgat, acc, rescue);
+            if (fullrow) return launch_sweep_rows<real, LPG, VPL, D, MINB, BLOCK, 0, true, false>(h, row, col, val, xown, xgat, acc, rescue);
+            if (hint == 1) return launch_sweep_rows<real, LPG, VPL, D, MINB, BLOCK, 1, false, false>(h, row, col, val, xown, xgat, acc, rescue);
+            if (hint == 2) return launch_sweep_rows<real, LPG, VPL, D, MINB, BLOCK, 2, false, false>(h, row, col, val, xown, xgat, acc, rescue);
+        } else if (h->strict && (fullrow || hint != 0)) {
+            return fail(HPF_EINVAL, "hint / fullrow variants of the register form are only built for the k<=64 fp32 row class");
+        }
+        return launch_sweep_rows<real, LPG, VPL, D, MINB, BLOCK, 0, false, false>(h, row, col, val, xown, xgat, acc, rescue);
+    }
 }
 
 struct RowsShape {
-    int lpg, block;
+    int lpg, depth, block, minb;
 };
-// measured defaults per fp32 row class (16-byte packs per row: 8 = k<=32, 16 = k<=64, 32 = k<=128)
-inline RowsShape default_rows_shape(int packs, int real_bytes) {
-    if (real_bytes == 4 && packs == 8) return RowsShape{4, 256};
-    if (real_bytes == 4 && packs == 16) return RowsShape{4, 128};
-    if (real_bytes == 4 && packs == 32) return RowsShape{8, 128};
-    return RowsShape{0, 0};
+// measured defaults per row class (16-byte packs per row: 8 = k<=32, 16 = k<=64, 32 = k<=128 in fp32)
+inline RowsShape default_rows_shape(int packs, int real_bytes, bool smem_gather) {
+    if (smem_gather) {
+        if (real_bytes == 4 && packs == 8) return RowsShape{4, 4, 256, 3};
+        if (real_bytes == 4 && packs == 16) return RowsShape{8, 4, 256, 3};
+        if (real_bytes == 4 && packs == 32) return RowsShape{8, 4, 128, 3};
+        if (real_bytes == 8 && packs == 32) return RowsShape{8, 4, 128, 3};
+    } else {
+        if (real_bytes == 4 && packs == 8) return RowsShape{8, 4, 256, 4};
+        if (real_bytes == 4 && packs == 16) return RowsShape{8, 2, 256, 4};
+        if (real_bytes == 4 && packs == 32) return RowsShape{16, 2, 256, 3};
+        if (real_bytes == 8 && packs == 32) return RowsShape{8, 2, 128, 3};
+    }
+    return RowsShape{0, 0, 0, 0};
 }
 
 template <typename C>
@@ -88,35 +104,37 @@ int launch_sweep_major(hpf_engine* h, const int* row, const int* col, const void
         rescue.direct_own = (real*)(own_is_user ? h->dirU : h->dirI);
         rescue.k = h->k;
     }
-    const RowsShape def = default_rows_shape(packs, (int)sizeof(real));
-    const int lpg = h->v_lpg ? h->v_lpg : def.lpg;
-    const int block = h->v_block ? h->v_block : def.block;
-    const int hint = h->v_hint >= 0 ? (h->v_hint ? 1 : 0) : 1;
     // FULLROW copies every pack of the row stride: only meaningful when the stride is the whole class width
     const bool full_ok = h->ld == packs * EPV;
-    const bool fullrow = full_ok && (h->v_fullrow >= 0 ? h->v_fullrow != 0 : false);
+    const bool smem_gather = h->v_smem_gather >= 0 ? h->v_smem_gather != 0 : (full_ok && !robust);
+    const bool fullrow = full_ok && (h->v_fullrow >= 0 ? h->v_fullrow != 0 : smem_gather);
+    const RowsShape def = default_rows_shape(packs, (int)sizeof(real), smem_gather);
+    const int lpg = h->v_lpg ? h->v_lpg : def.lpg, depth = h->v_depth ? h->v_depth : def.depth;
+    const int block = h->v_block ? h->v_block : def.block, minb = h->v_minb ? h->v_minb : def.minb;
+    const int hint = h->v_hint >= 0 ? h->v_hint : kDefaultHint;
     if (h->chunk % 32 != 0 || h->chunk > kMaxChunk)
         return fail(HPF_EINVAL, "chunk must be a multiple of 32 and <= %d (got %d)", kMaxChunk, h->chunk);
-#define HPF_S(L, B)                                                                                         \
-    if (lpg == L && block == B)                                                                             \
-        return launch_sweep_rows_flags<real, L, packs / L, smem_ctas<packs / L, B>(), B, packs == 16 && sizeof(real) == 4>( \
-            h, row, col, val, xown, xgat, acc, rescue, hint, fullrow, robust);
+#define HPF_S(L, D, B, M)                                                                                       \
+    if (lpg == L && depth == D && block == B && minb == M)                                                      \
+        return launch_sweep_rows_flags<real, L, packs / L, D, M, B, packs == 16 && sizeof(real) == 4>(          \
+            h, row, col, val, xown, xgat, acc, rescue, hint, fullrow, smem_gather, robust);
     if constexpr (packs == 8 && sizeof(real) == 4) {
-        HPF_S(4, 256) HPF_S(4, 128) HPF_S(8, 256)
+        HPF_S(4, 4, 256, 3) HPF_S(8, 4, 256, 4) HPF_S(8, 2, 256, 4) HPF_S(8, 4, 128, 6) HPF_S(4, 4, 256, 2) HPF_S(4, 4, 128, 6)
     }
     if constexpr (packs == 16 && sizeof(real) == 4) {
-        HPF_S(4, 128) HPF_S(8, 256) HPF_S(8, 128) HPF_S(4, 64)
+        HPF_S(8, 4, 256, 3) HPF_S(8, 2, 256, 4) HPF_S(8, 4, 128, 6) HPF_S(8, 4, 256, 2) HPF_S(8, 2, 256, 3)
+        HPF_S(16, 4, 256, 4) HPF_S(4, 4, 128, 4) HPF_S(8, 8, 128, 4)
     }
     if constexpr (packs == 32 && sizeof(real) == 4) {
-        HPF_S(8, 128) HPF_S(16, 256) HPF_S(16, 128) HPF_S(8, 64)
+        HPF_S(8, 4, 128, 3) HPF_S(16, 4, 256, 3) HPF_S(16, 2, 256, 3) HPF_S(8, 2, 128, 4) HPF_S(8, 4, 128, 2)
     }
     if constexpr (packs == 32 && sizeof(real) == 8) {
-        HPF_S(8, 128) HPF_S(16, 128)
+        HPF_S(8, 4, 128, 3) HPF_S(16, 4, 128, 4) HPF_S(8, 2, 128, 3) HPF_S(16, 2, 128, 4)
     }
 #undef HPF_S
-    if (h->strict && (h->v_lpg || h->v_block))
-        return fail(HPF_EINVAL, "no such sweep shape for this row class (lpg=%d block=%d)", lpg, block);
-    // generic shape of the classes without a measured table entry (fp64, rows beyond 512 bytes)
-    return launch_sweep_rows_flags<real, C::lpg, C::vpl, smem_ctas<C::vpl, 128>(), 128, false>(h, row, col, val, xown, xgat, acc,
-                                                                                               rescue, hint, fullrow, robust);
+    if (h->strict && (h->v_lpg || h->v_block || h->v_depth || h->v_minb))
+        return fail(HPF_EINVAL, "no such sweep shape for this row class (lpg=%d depth=%d block=%d minb=%d)", lpg, depth, block, minb);
+    // generic shape of the classes without a measured table entry: the class's lane-group width, 2 rows in flight
+    return launch_sweep_rows_flags<real, C::lpg, C::vpl, 2, 2, 128, false>(h, row, col, val, xown, xgat, acc, rescue, hint,
+                                                                          fullrow, smem_gather, robust);
 }

@@ -68,7 +68,10 @@ def run_sharded_iterations(engine, niter, partial_tensors=None, group=None, all_
     if all_reduce is None:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             def all_reduce(t):
-                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+                if t.is_cuda:
+                    _all_reduce_device(t, group)
+                else:
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
         else:
             def all_reduce(t):
                 return None
@@ -93,13 +96,39 @@ def run_sharded_iterations_overlapped(engine, niter, partial_tensors=None, group
     t_items, t_theta = partial_tensors
     for _ in range(int(niter)):
         engine.sweep_side(0)
-        w_items = dist.all_reduce(t_items, op=dist.ReduceOp.SUM, group=group, async_op=True)
+        w_items = _all_reduce_device(t_items, group, async_op=True)
         engine.sweep_side(1)
         engine.update_users()
-        w_theta = dist.all_reduce(t_theta, op=dist.ReduceOp.SUM, group=group, async_op=True)
-        w_items.wait()
-        w_theta.wait()
+        w_theta = _all_reduce_device(t_theta, group, async_op=True)
+        for w in (w_items, w_theta):
+            if w is not None:
+                w.wait()
         engine.update_items()
+
+
+def _all_reduce_device(t, group=None, async_op=False):
+    """SUM all-reduce of a device tensor.  With NCCL it is the collective itself; with a CPU backend (gloo:
+    the 2-ranks-on-one-GPU test set-up, where NCCL refuses duplicate devices) it is staged through the host."""
+    import torch.distributed as dist
+    if dist.get_backend(group) == "nccl":
+        return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+    host = t.cpu()
+    dist.all_reduce(host, op=dist.ReduceOp.SUM, group=group)
+    t.copy_(host)
+    return None
+
+
+def _all_gather_bytes(payload, group=None):
+    """All-gather of one equal-length bytes object per rank (CPU or NCCL backend)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    mine = torch.frombuffer(bytearray(payload), dtype=torch.uint8)
+    if dist.get_backend(group) == "nccl":
+        mine = mine.cuda()
+    allh = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allh, mine, group=group)
+    return [bytes(t.cpu().numpy().tobytes()) for t in allh]
 
 
 def attach_peers(engine, group=None):
@@ -108,10 +137,7 @@ def attach_peers(engine, group=None):
     import torch
     import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    mine = torch.frombuffer(bytearray(engine.peer_export()), dtype=torch.uint8).cuda()
-    allh = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(allh, mine, group=group)
-    engine.peer_attach(rank, world, b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh))
+    engine.peer_attach(rank, world, b"".join(_all_gather_bytes(engine.peer_export(), group)))
 
 
 def run_sharded_iterations_peer(engine, niter, group=None, materialize_last=True):
@@ -128,62 +154,159 @@ def run_sharded_iterations_peer(engine, niter, group=None, materialize_last=True
     t_theta = wrap_device_buffer(p_theta, n_theta, torch.float64, dev)
     t_beta = wrap_device_buffer(p_beta, n_beta, torch.float64, dev)
     for it in range(int(niter)):
+        last = materialize_last and it == niter - 1
         engine.sweep_side(0)
         engine.sweep_side(1)
-        engine.update_users()
-        dist.all_reduce(t_theta, op=dist.ReduceOp.SUM, group=group)
-        engine.update_items_peer(materialize_last and it == niter - 1)
-        dist.all_reduce(t_beta, op=dist.ReduceOp.SUM, group=group)
+        engine.update_users(last)
+        _all_reduce_device(t_theta, group)
+        engine.update_items_peer(last)
+        _all_reduce_device(t_beta, group)
         engine.peer_finish()
 
 
-class GraphedShardLoop:
-    """One user-sharded iteration (kernels + NCCL collectives) captured ONCE into a CUDA graph and
-    replayed, so that the per-iteration host cost is a single graph launch instead of ~7 Python ->
-    C / c10d calls (at 8 GPUs the iteration is < 1 ms and the eager loop is host-bound).
-    mode: "peer" (fused NVLink exchange, needs attach_peers), "overlap" or "plain" (NCCL all-reduce)."""
+class ShardedLoop:
+    """Iteration driver of one user shard: picks the item-side exchange and, optionally, replays one captured
+    iteration as a CUDA graph (kernels + collectives) so that the per-iteration host cost is a single graph
+    launch instead of ~9 Python -> C / c10d calls.
 
-    def __init__(self, engine, mode="peer", group=None):
+    mode: "peer"    fused reduce-scatter + item update + all-gather kernel over NVLink peer memory (CUDA IPC)
+          "overlap" NCCL all-reduce of the item-side partial sums, overlapping the user-major pass
+          "plain"   NCCL all-reduce after both passes
+          "auto"    "peer"
+    Construct it BEFORE hpf_load_state (the peer mode maps the engine's item-side buffers into every rank)."""
+
+    def __init__(self, engine, mode="auto", group=None, graph=False):
         import torch
-        self.engine, self.mode, self.group = engine, mode, group
-        self.stream = torch.cuda.Stream()
+        import torch.distributed as dist
+        self.engine, self.group = engine, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if mode == "auto":
+            mode = "peer"
+        if self.world == 1:
+            mode = "single"
+        if mode not in ("peer", "overlap", "plain", "single"):
+            raise ValueError("unknown exchange mode %r" % (mode,))
+        self.mode = mode
+        self.use_graph = bool(graph) and self.world > 1
+        self.stream = torch.cuda.Stream() if self.use_graph else torch.cuda.current_stream()
         self.graph = None
         self.launches_per_replay = 0   # engine kernels inside one captured iteration
         self.replayed_launches = 0     # kernels launched through graph replays (the engine cannot count those)
-        engine.set_stream(self.stream)
+        if self.use_graph:
+            engine.set_stream(self.stream)
+        if engine.describe().get("robust") == "1" and self.world > 1:
+            raise ValueError("robust mode (tiny shape priors) is not available for sharded runs")
         if mode == "peer":
             attach_peers(engine, group)
 
-    def _one(self, materialize):
-        if self.mode == "peer":
-            run_sharded_iterations_peer(self.engine, 1, self.group, materialize_last=materialize)
+    def _iterations(self, n, materialize_last):
+        if self.mode == "single":
+            self.engine.step_full(n)
+        elif self.mode == "peer":
+            run_sharded_iterations_peer(self.engine, n, self.group, materialize_last=materialize_last)
         elif self.mode == "overlap":
-            run_sharded_iterations_overlapped(self.engine, 1, group=self.group)
+            run_sharded_iterations_overlapped(self.engine, n, group=self.group)
         else:
-            run_sharded_iterations(self.engine, 1, group=self.group)
+            run_sharded_iterations(self.engine, n, group=self.group)
 
     def run(self, niter):
-        """`niter` iterations; the last one runs eagerly so that shape/rate matrices are materialised."""
+        """`niter` iterations; with a graph, the last one runs eagerly so that shape/rate matrices are materialised."""
         import torch
         niter = int(niter)
         if niter <= 0:
+            return
+        if not self.use_graph:
+            self._iterations(niter, True)
             return
         cur = torch.cuda.current_stream()
         self.stream.wait_stream(cur)
         with torch.cuda.stream(self.stream):
             if self.graph is None and niter > 1:
-                self._one(False)            # warm-up (NCCL channels, lazy allocations) before capture
+                self._iterations(1, False)   # warm-up (NCCL channels, lazy allocations) before capture
                 niter -= 1
-                torch.cuda.synchronize()
+                self.stream.synchronize()
                 g = torch.cuda.CUDAGraph()
                 before = self.engine.launch_count
-                with torch.cuda.graph(g, stream=self.stream):
-                    self._one(False)
+                with torch.cuda.graph(g, stream=self.stream, capture_error_mode="thread_local"):
+                    self._iterations(1, False)
                 self.launches_per_replay = self.engine.launch_count - before
                 self.graph = g
-                self.engine.set_stream(self.stream)
             for _ in range(niter - 1):
                 self.graph.replay()
                 self.replayed_launches += self.launches_per_replay
-            self._one(True)
+            if niter >= 1:
+                self._iterations(1, True)
         cur.wait_stream(self.stream)
+
+    def close(self):
+        self.graph = None
+
+
+def sharded_parity_check(local_device, options=None, nU=60_000, nI=25_000, nnz=1_500_000, k=50, its=3, mode=None,
+                         graph=False, group=None):
+    """Driver-visible proof of the multi-GPU data plane (run by bench.py before it times anything at N>1):
+    `its` fp64 iterations of a down-scaled problem, user-sharded over all ranks with the SAME exchange the
+    bench is about to time, against one engine on rank 0.  Checks (i) every state array <= 1e-10 relative,
+    (ii) the item-side replicas bit-identical across ranks.  Returns a dict for the JSON line; raises on failure."""
+    import os
+    import torch
+    import torch.distributed as dist
+    import bench
+    from .engine import Engine
+    from .loops import CudaLoops
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = torch.device("cuda", local_device)
+    mode = mode or os.environ.get("HPF_MULTI", "auto")
+    u, i, y = bench.synth_coo_torch(nU, nI, nnz, dev, seed=7)
+    y = y.to(torch.float64)
+    loops = CudaLoops(False, device=local_device)
+    Gs, Gr, Ls, Lr, kr, tr = loops.initialize_parameters(np.empty((nU, k)), np.empty((nI, k)), 123, 0.3, 0.3, 1.0, 0.3, 0.3, 1.0)
+    cuts = plan_user_shards(u, nU, world)
+    lo, hi = cuts[rank], cuts[rank + 1]
+    lu, li, ly = (t.contiguous() for t in shard_triples(u, i, y, lo, hi))
+    eng = Engine(hi - lo, nI, k, 8, local_device)
+    for name, val in (options or {}).items():
+        eng.set_option(name, val)
+    loop = ShardedLoop(eng, mode=mode, graph=graph, group=group)
+    eng.load_state(np.ascontiguousarray(Gs[lo:hi]), np.ascontiguousarray(Gr[lo:hi]), Ls, Lr, np.ascontiguousarray(kr[lo:hi]), tr)
+    eng.load_coo(lu, li, ly)
+    loop.run(its)
+    torch.cuda.synchronize()
+    mine = eng.export_all()
+    loop.close()
+    eng.close()
+    cdev = dev if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    beta = torch.from_numpy(mine["Beta"]).to(cdev)
+    ref_beta = beta.clone()
+    dist.broadcast(ref_beta, 0, group=group)
+    same = torch.tensor([1 if torch.equal(beta, ref_beta) else 0], device=cdev)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN, group=group)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (lo, mine["Theta"], mine["k_rte"], mine["Gamma_shp"]), group=group)
+    result = None
+    if rank == 0:
+        e1 = Engine(nU, nI, k, 8, local_device)
+        e1.load_state(Gs, Gr, Ls, Lr, kr, tr)
+        e1.load_coo(u.contiguous(), i.contiguous(), y.contiguous())
+        e1.step_full(its)
+        single = e1.export_all()
+        e1.close()
+        parts = sorted(gathered, key=lambda t: t[0])
+
+        def rel(x, ref):
+            return float(np.max(np.abs(x - ref) / np.maximum(np.abs(ref), 1e-300)))
+        errs = dict(Theta=rel(np.concatenate([p[1] for p in parts]), single["Theta"]),
+                    k_rte=rel(np.concatenate([p[2] for p in parts]), single["k_rte"]),
+                    Gamma_shp=rel(np.concatenate([p[3] for p in parts]), single["Gamma_shp"]),
+                    Beta=rel(mine["Beta"], single["Beta"]), Lambda_shp=rel(mine["Lambda_shp"], single["Lambda_shp"]),
+                    Lambda_rte=rel(mine["Lambda_rte"], single["Lambda_rte"]), t_rte=rel(mine["t_rte"], single["t_rte"]))
+        result = {"what": "%d fp64 iterations of %dx%dx%d k=%d sharded over %d GPUs (exchange=%s%s) vs one engine"
+                          % (its, nU, nI, nnz, k, world, loop.mode, ", graph replay" if graph else ""),
+                  "max_rel_err": max(errs.values()), "errors": errs, "tolerance": 1e-10,
+                  "item_replicas_bit_identical": bool(int(same.item()) == 1)}
+        result["ok"] = bool(result["max_rel_err"] < 1e-10 and result["item_replicas_bit_identical"])
+    box = [result]
+    dist.broadcast_object_list(box, 0, group=group)
+    if not box[0]["ok"]:
+        raise RuntimeError("multi-GPU parity check FAILED: %r" % (box[0],))
+    return box[0]

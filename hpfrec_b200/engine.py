@@ -165,8 +165,8 @@ class Engine:
         """side 0: item-major pass (item-side partial sums), side 1: user-major pass."""
         _lib.check(self._lib.hpf_sweep_side(self._h, int(side)))
 
-    def update_users(self):
-        _lib.check(self._lib.hpf_update_users(self._h))
+    def update_users(self, materialize=True):
+        _lib.check(self._lib.hpf_update_users_ex(self._h, int(bool(materialize))))
 
     def update_items(self):
         _lib.check(self._lib.hpf_update_items(self._h))
@@ -221,6 +221,12 @@ class Engine:
                                                 int(bool(user_batch)), float(rho), float(mult),
                                                 int(bool(blend_all_rates))))
 
+    def step_epoch_ids(self, ids, batch_rows, user_batch, rho):
+        """One SVI epoch: consecutive slices of `batch_rows` ids of the (shuffled) list are the minibatches.
+        Asynchronous: returns with the epoch's kernels in flight on the engine's stream."""
+        _lib.check(self._lib.hpf_step_epoch_ids(self._h, _ptr(ids, name="ids"), int(ids.shape[0]), _index_bytes(ids),
+                                                int(batch_rows), int(bool(user_batch)), float(rho)))
+
     # -- metrics / scoring --------------------------------------------------------------------------
     def llk(self, ix_u, ix_i, Y, full_llk=False):
         out = (ctypes.c_double * 4)()
@@ -261,3 +267,68 @@ def digamma(x, device=0):
     out = np.empty_like(x)
     _lib.check(lib.hpf_digamma(x.dtype.itemsize, int(device), _ptr(x), _ptr(out), int(x.size)))
     return out
+
+
+class Scorer:
+    """Theta and Beta resident on the device (hpf_scorer_*): predict / llk / topN of a fitted model without
+    re-uploading the factors per call."""
+
+    def __init__(self, Theta, Beta, device=0):
+        self._lib = _lib.load()
+        self._h = ctypes.c_void_p()
+        Theta = np.ascontiguousarray(Theta)
+        Beta = np.ascontiguousarray(Beta, dtype=Theta.dtype)
+        if Theta.dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
+            raise TypeError("Theta/Beta must be float32 or float64")
+        self.dtype = Theta.dtype
+        self.nU, self.k = Theta.shape
+        self.nI = Beta.shape[0]
+        _lib.check(self._lib.hpf_scorer_create(ctypes.byref(self._h), _ptr(Theta), _ptr(Beta), self.nU, self.nI,
+                                               self.k, self.dtype.itemsize, int(device)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.hpf_scorer_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def predict(self, ix_u, ix_i):
+        ix_u, ix_i = as_index(ix_u), as_index(ix_i)
+        if ix_i.dtype != ix_u.dtype:
+            ix_i = ix_i.astype(ix_u.dtype)
+        out = np.empty(ix_u.shape[0], dtype=self.dtype)
+        _lib.check(self._lib.hpf_scorer_predict(self._h, _ptr(ix_u), _ptr(ix_i), int(ix_u.shape[0]), _index_bytes(ix_u),
+                                                _ptr(out)))
+        return out
+
+    def llk(self, ix_u, ix_i, Y, full_llk=False):
+        """[sum Y log yhat (- lgamma(Y+1) if full_llk), sum (Y - yhat)^2, sum yhat]"""
+        ix_u, ix_i = as_index(ix_u), as_index(ix_i)
+        if ix_i.dtype != ix_u.dtype:
+            ix_i = ix_i.astype(ix_u.dtype)
+        Y = np.ascontiguousarray(Y, dtype=self.dtype)
+        out = (ctypes.c_double * 3)()
+        _lib.check(self._lib.hpf_scorer_llk(self._h, _ptr(ix_u), _ptr(ix_i), _ptr(Y), int(Y.shape[0]), _index_bytes(ix_u),
+                                            int(bool(full_llk)), out))
+        return list(out)
+
+    def topn(self, user, n, pool=None, seen=None, with_scores=False):
+        """Item rows of the n best items for user row `user`, best first (see hpf_scorer_topn)."""
+        n = int(n)
+        pool = None if pool is None else as_index(pool).astype(np.int64)
+        seen = None if seen is None or len(seen) == 0 else as_index(seen).astype(np.int64)
+        ids = np.empty(max(n, 1), dtype=np.int64)
+        scores = np.empty(max(n, 1), dtype=self.dtype)
+        n_out = ctypes.c_int32()
+        _lib.check(self._lib.hpf_scorer_topn(
+            self._h, int(user), n, _ptr(pool), 0 if pool is None else int(pool.shape[0]), _ptr(seen),
+            0 if seen is None else int(seen.shape[0]), 8, ids.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), _ptr(scores),
+            ctypes.byref(n_out)))
+        ids, scores = ids[:n_out.value], scores[:n_out.value]
+        return (ids, scores) if with_scores else ids
+

@@ -100,6 +100,27 @@ class CudaLoops:
         X = coo_array((Y, (ix_u, ix_i)), shape=(nU, nI)).tocsc()
         return X.indptr.astype(np.int64), X.indices.astype(np.int64), X.data.astype(self.dtype)
 
+    # ---- SVI epochs (pxi:262-377) ---------------------------------------------------------------------------
+    def svi_epochs(self, eng, svi, n_epochs, nU, nI, users_per_batch, items_per_batch, step_size=None):
+        """`n_epochs` epochs of the reference's minibatch schedule on a loaded engine.  `svi` carries what persists
+        between epochs: the PCG64 generator (pxi:207), the in-place shuffled id lists (pxi:277, 329) and the epoch
+        counter.  Epoch e is a USER epoch iff both sizes are set and (e+1) % 2 == 0, or only users_per_batch is set
+        (pxi:265-273).  Every minibatch is assembled and applied on the device (hpf_step_batch_ids)."""
+        dt = self.dtype
+        if step_size is None:
+            step_size = lambda x: 1 / np.sqrt(x + 2)   # the constructor default (hpfrec/__init__.py:208)
+        for _ in range(int(n_epochs)):
+            e = svi["epoch"]
+            rho = float(dt.type(step_size(e)))                                       # pxi:263
+            if users_per_batch > 0 and items_per_batch > 0:
+                user_epoch = ((e + 1) % 2) == 0                                      # pxi:265-269
+            else:
+                user_epoch = users_per_batch > 0
+            ids, n, per = (svi["users"], nU, users_per_batch) if user_epoch else (svi["items"], nI, items_per_batch)
+            svi["rng"].shuffle(ids)                                                  # pxi:277 / 329
+            eng.step_epoch_ids(ids, per, user_epoch, rho)
+            svi["epoch"] = e + 1
+
     # ---- fit_hpf (pxi:147-418) -----------------------------------------------------------------------
     def fit_hpf(self, a, a_prime, b_prime, c, c_prime, d_prime, Y, ix_u, ix_i, Theta, Beta,
                 maxiter, stop_crit, check_every, stop_thr, users_per_batch, items_per_batch,
@@ -138,16 +159,11 @@ class CudaLoops:
             eng.load_coo(ix_u, ix_i, Y)
             t_ingest = time.time() - t_ingest
 
-            if items_per_batch > 0:
-                if verbose:
-                    print("Creating item indices for stochastic optimization...")
-                items_numeration = np.arange(nI, dtype=np.int64)
-                nbatches_i = int(np.ceil(float(nI) / float(items_per_batch)))
-            if users_per_batch != 0:
-                users_numeration = np.arange(nU, dtype=np.int64)
-                nbatches_u = int(np.ceil(float(nU) / float(users_per_batch)))
-
-            rng = np.random.default_rng(seed=random_seed if random_seed > 0 else None)   # pxi:207
+            if items_per_batch > 0 and verbose:
+                print("Creating item indices for stochastic optimization...")
+            # shuffled id lists persist across epochs; the generator is PCG64 seeded like pxi:207
+            svi = dict(rng=np.random.default_rng(seed=random_seed if random_seed > 0 else None),
+                       users=np.arange(nU, dtype=np.int64), items=np.arange(nI, dtype=np.int64), epoch=0)
             errs = [0.0, 0.0]
             last_crit = -np.inf
             Theta_prev = None
@@ -177,24 +193,7 @@ class CudaLoops:
                     eng.step_full(burst)
                     it_done += burst
                 else:
-                    e = it_done
-                    rho = float(dt.type(step_size(e)))
-                    if users_per_batch > 0 and items_per_batch > 0:
-                        user_epoch = ((e + 1) % 2) == 0                                 # pxi:265-269
-                    else:
-                        user_epoch = users_per_batch > 0
-                    if user_epoch:
-                        rng.shuffle(users_numeration)                                    # pxi:277
-                        for bt in range(nbatches_u):
-                            users = users_numeration[bt * users_per_batch: min(nU, (bt + 1) * users_per_batch)]
-                            mult = float(nU) / float(users.shape[0])                     # pxi:282
-                            eng.step_batch_ids(np.ascontiguousarray(users), True, rho, mult, False)
-                    else:
-                        rng.shuffle(items_numeration)                                    # pxi:329
-                        for bt in range(nbatches_i):
-                            items = items_numeration[bt * items_per_batch: min(nI, (bt + 1) * items_per_batch)]
-                            mult = float(nI) / float(items.shape[0])                     # pxi:334
-                            eng.step_batch_ids(np.ascontiguousarray(items), False, rho, mult, False)
+                    self.svi_epochs(eng, svi, 1, nU, nI, users_per_batch, items_per_batch, step_size)
                     it_done += 1
                 i = it_done - 1
 

@@ -108,6 +108,10 @@ int hpf_sweep(hpf_engine* h);
  * overlap), side 1 = user-major pass. */
 int hpf_sweep_side(hpf_engine* h, int32_t side);
 int hpf_update_users(hpf_engine* h);
+/* materialize == 0: keep only what the next iteration needs (per-row factors, k_rte, column sums) and skip the
+ * stores of Gamma_shp / Gamma_rte, exactly like the intermediate iterations of hpf_step_full; the LAST
+ * iteration before an export must materialize. */
+int hpf_update_users_ex(hpf_engine* h, int32_t materialize);
 int hpf_update_items(hpf_engine* h);
 int hpf_partials(hpf_engine* h, void** item_sums, int64_t* item_sums_count, void** theta_colsum,
                  int64_t* theta_colsum_count);
@@ -152,6 +156,14 @@ int hpf_step_batch(hpf_engine* h, const void* ix_u, const void* ix_i, const void
 int hpf_step_batch_ids(hpf_engine* h, const void* ids, int64_t n_ids, int32_t index_bytes,
                        int32_t user_batch, double rho, double mult, int32_t blend_all_rates);
 
+/* One whole SVI epoch of fit_hpf (user epoch pxi:275-325 when user_batch != 0, else item epoch pxi:329-377):
+ * `ids` is the shuffled id list of the batched side (pxi:277 / 329); consecutive slices of `batch_rows` ids are
+ * the minibatches, each applied like hpf_step_batch_ids with multiplier n / |batch| (pxi:282 / 334) and
+ * blend_all_rates = 0.  The list crosses to the device once and nothing inside waits for the device: the call
+ * returns with the epoch's kernels in flight on the engine's stream.  ids: [h|d]. */
+int hpf_step_epoch_ids(hpf_engine* h, const void* ids, int64_t n_ids, int32_t index_bytes,
+                       int64_t batch_rows, int32_t user_batch, double rho);
+
 /* ---- convergence metrics and scoring --------------------------- */
 
 /* llk_plus_rmse (pxi:627) over the given triples using the engine's current Theta/Beta:
@@ -165,6 +177,29 @@ int hpf_llk_train(hpf_engine* h, int32_t full_llk, double out[4]);
 /* predict_multiple (pxi:803): out[n] = Theta[ix_u[n]] . Beta[ix_i[n]].  [h|d] */
 int hpf_predict(hpf_engine* h, const void* ix_u, const void* ix_i, int64_t n, int32_t index_bytes,
                 void* out);
+
+/* ---- device-resident scoring of a fitted model -------------------------- */
+
+/* Holds Theta (nU x k) and Beta (nI x k) -- the two arrays HPF.predict / eval_llk / topN read
+ * (hpfrec/__init__.py:1198-1446) -- on the device, so repeated scoring calls do not re-upload them.  [h|d] */
+typedef struct hpf_scorer hpf_scorer;
+int hpf_scorer_create(hpf_scorer** out, const void* Theta, const void* Beta, int64_t nU, int64_t nI,
+                      int32_t k, int32_t real_bytes, int32_t device);
+int hpf_scorer_destroy(hpf_scorer* s);
+/* predict_multiple (pxi:803-810): out[n] = Theta[ix_u[n]] . Beta[ix_i[n]].  [h|d] */
+int hpf_scorer_predict(hpf_scorer* s, const void* ix_u, const void* ix_i, int64_t n, int32_t index_bytes,
+                       void* out);
+/* llk_plus_rmse + sum_prediction (pxi:627-658, 816-825): out[0] = sum Y log yhat [- lgamma(Y+1)],
+ * out[1] = sum (Y - yhat)^2, out[2] = sum yhat; calc_llk (pxi:525-534) is out[0] - out[2].  [h|d] */
+int hpf_scorer_llk(hpf_scorer* s, const void* ix_u, const void* ix_i, const void* Y, int64_t n,
+                   int32_t index_bytes, int32_t full_llk, double out[3]);
+/* HPF.topN (hpfrec/__init__.py:1296-1396): the n best item rows for user row `user` by Theta[user] . Beta[i],
+ * best first, restricted to `pool` (n_pool item rows, NULL = all items) and without the rows in `seen`
+ * (NULL = keep all).  out_ids (host, n entries) receives item rows, out_scores (host, `real`, may be NULL)
+ * their scores, *n_out how many were written (fewer than n when the pool runs out).  pool/seen: [h|d]. */
+int hpf_scorer_topn(hpf_scorer* s, int64_t user, int32_t n, const void* pool, int64_t n_pool,
+                    const void* seen, int64_t n_seen, int32_t index_bytes, int64_t* out_ids,
+                    void* out_scores, int32_t* n_out);
 
 /* ---- stateless one-shot forms over caller buffers ([h|d]) of the reference's L1 loops ------ */
 

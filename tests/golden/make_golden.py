@@ -206,6 +206,15 @@ def api_golden():
     new = new.loc[new.Count > 0].reset_index(drop=True)
     out["new_items"], out["new_counts"] = new.ItemId.to_numpy(), new.Count.to_numpy()
     out["new_factors"] = m2.predict_factors(new.copy(), maxiter=10, random_seed=1)
+    # add_user (hpfrec/__init__.py:1060-1196) on the same fitted model: a NEW user from the same data.  The reference
+    # passes cast_int(stop_thr) = 0 to calc_user_factors on this path (init:1153), i.e. it always runs `maxiter` iterations.
+    m2.add_user(user_id=100, counts_df=new.copy(), update_existing=False, maxiter=10, random_seed=1)
+    out["adduser_Theta_last"] = m2.Theta[-1].copy()
+    out["adduser_nusers"] = m2.nusers
+    out["adduser_n_seen_last"] = int(m2._n_seen_by_user[-1])
+    out["adduser_st_ix_last"] = int(m2._st_ix_user[-1])
+    out["adduser_seen_tail"] = np.array(m2.seen[int(m2._st_ix_user[-1]):], dtype=np.int64)
+    out["adduser_topn"] = np.array(m2.topN(user=100, n=5, exclude_seen=True), dtype=np.int64)
     # SVI through the class (ncores=1 for determinism)
     m5 = HPF(k=8, use_float=False, random_seed=7, maxiter=6, verbose=False, ncores=1, users_per_batch=20,
              items_per_batch=30, reindex=False, check_every=None)

@@ -323,29 +323,44 @@ def test_wide_rows_vs_oracle(k, dtype):
         assert relerr(out[key], ref[key]) < tol, key
 
 
-# every compiled shape of sweep_rows_kernel per row class: (lanes per row, CTA size)
-SHAPES = {10: [(0, 0)], 30: [(4, 256), (4, 128), (8, 256)], 50: [(4, 128), (8, 256), (8, 128), (4, 64)],
-          128: [(8, 128), (16, 256), (16, 128), (8, 64)]}
+# every compiled shape of sweep_rows_kernel per row class: (lanes per row, rows in flight, CTA size, CTAs per SM)
+SHAPES = {(10, 8): [(0, 0, 0, 0)],
+          (30, 4): [(4, 4, 256, 3), (8, 4, 256, 4), (8, 2, 256, 4), (8, 4, 128, 6), (4, 4, 256, 2), (4, 4, 128, 6)],
+          (50, 4): [(8, 4, 256, 3), (8, 2, 256, 4), (8, 4, 128, 6), (8, 4, 256, 2), (8, 2, 256, 3), (16, 4, 256, 4),
+                    (4, 4, 128, 4), (8, 8, 128, 4)],
+          (128, 4): [(8, 4, 128, 3), (16, 4, 256, 3), (16, 2, 256, 3), (8, 2, 128, 4), (8, 4, 128, 2)],
+          (50, 8): [(8, 4, 128, 3), (16, 4, 128, 4), (8, 2, 128, 3), (16, 2, 128, 4)]}
 
 
-@pytest.mark.parametrize("k,dtype", [(10, np.float64), (50, np.float32), (30, np.float32), (128, np.float32)])
+@pytest.mark.parametrize("k,dtype", [(10, np.float64), (50, np.float32), (30, np.float32), (128, np.float32),
+                                     (50, np.float64)])
 def test_sweep_shapes_vs_oracle(golden_full, k, dtype):
-    """Every compiled lane-group shape of the sweep kernel, with and without L2 policies, with whole-stride
-    copies (fullrow) where the row class has them, computes the same iterations as the oracle."""
+    """Every compiled lane-group shape of the sweep kernel in both production forms (shared-memory ring with
+    whole-stride copies; register gathers), plus the measurement variants of the headline row class (L2-policy
+    modes, prefetch, the ring without whole-stride copies): the same iterations as the oracle."""
     g = golden_full
     st0 = O.initialize_parameters(100, 100, k, 123, 0.3, 1.0, 0.3, 1.0, dtype)
     ref = {k_: v.astype(np.float64) for k_, v in st0.items()}
     for _ in range(3):
         O.cavi_full_iteration(ref, g["Y"], g["ix_u"], g["ix_i"], **HYP)
     tol = 1e-11 if dtype == np.float64 else 3e-5
-    for lpg, block in SHAPES[k]:
-        for hint, fullrow in ((1, 0), (0, 0), (1, 1), (0, 1)):
-            if k != 50 and (hint, fullrow) != (1, 0):
-                continue   # the measurement variants are only built for the headline row class
-            out = _fit_gpu(g["Y"], g["ix_u"], g["ix_i"], 100, 100, k, 3, 123, dtype=dtype, lpg=lpg, block=block, hint=hint,
-                           fullrow=fullrow, strict=1, chunk=64, panel_mb=0.004)
+    headline = (k, dtype) == (50, np.float32)
+    for lpg, depth, block, minb in SHAPES[(k, np.dtype(dtype).itemsize)]:
+        variants = [dict(smem_gather=1, fullrow=1, hint=0)]
+        if depth <= 4:
+            variants.append(dict(smem_gather=0, fullrow=0, hint=0))
+            if headline:
+                variants += [dict(smem_gather=0, fullrow=0, hint=1), dict(smem_gather=0, fullrow=0, hint=2),
+                             dict(smem_gather=0, fullrow=1, hint=0), dict(smem_gather=0, fullrow=0, hint=0, prefetch=1)]
+        if headline:
+            variants += [dict(smem_gather=1, fullrow=1, hint=2), dict(smem_gather=1, fullrow=0, hint=0)]
+        if k == 10:
+            variants = [dict(), dict(smem_gather=0)]
+        for var in variants:
+            out = _fit_gpu(g["Y"], g["ix_u"], g["ix_i"], 100, 100, k, 3, 123, dtype=dtype, lpg=lpg, depth=depth, block=block,
+                           minb=minb, strict=1, chunk=64, panel_mb=0.004, **var)
             for key in STATE_KEYS:
-                assert relerr(out[key], ref[key]) < tol, (key, lpg, block, hint, fullrow)
+                assert relerr(out[key], ref[key]) < tol, (key, lpg, depth, block, minb, var)
 
 
 def test_step_batch_ids_equals_explicit_batch(golden_full):

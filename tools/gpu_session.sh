@@ -15,7 +15,7 @@ python -c "import os; print('cpus', len(os.sched_getaffinity(0)))" > $OUT/host.t
 
 if has test; then
 log "parity tests"
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_refscale.py tests/test_gpu_api.py -m gpu -q -x > $OUT/pytest_parity.log 2>&1
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_refscale.py tests/test_gpu_api.py -m gpu -q > $OUT/pytest_parity.log 2>&1
 log "  rc=$? $(tail -1 $OUT/pytest_parity.log)"
 fi
 if has tune; then
@@ -30,14 +30,24 @@ timeout 100 tools/bin/tma_gather_probe --rows 380000 > $OUT/tma_gather_probe_ite
 log "  rc=$? $(wc -l < $OUT/tma_gather_probe_users.jsonl) + $(wc -l < $OUT/tma_gather_probe_items.jsonl) lines"
 fi
 if has ncu; then
-for CFG in ${NCU_CFGS:-"lpg=4,block=128" "lpg=8,block=256"}; do
+for CFG in ${NCU_CFGS:-"chunk=256"}; do
 TAG=$(echo $CFG | tr ',=' '__')
 log "ncu --set full, $CFG"
 OPTS=""; for o in $(echo $CFG | tr ',' ' '); do OPTS="$OPTS --option $o"; done
 timeout 240 ncu --set full --clock-control none --import-source on -k regex:'sweep_rows|update_rows' -s 8 -c 4 \
     -f -o $OUT/ncu_full_$TAG python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline $OPTS > $OUT/ncu_full_$TAG.log 2>&1
 log "  rc=$?"
+# gpurun_out/ is capped at 64 MiB: keep the raw and source pages as CSV, drop the report itself
+ncu -i $OUT/ncu_full_$TAG.ncu-rep --page raw --csv > $OUT/ncu_full_$TAG.raw.csv 2>/dev/null
+ncu -i $OUT/ncu_full_$TAG.ncu-rep --page source --csv -k regex:sweep_rows -c 1 > $OUT/ncu_full_$TAG.source.csv 2>/dev/null
+rm -f $OUT/ncu_full_$TAG.ncu-rep
 done
+fi
+if has traffic; then
+log "DRAM traffic probe (ncu metrics)"
+timeout 400 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,gpu__time_duration.sum \
+    --clock-control none -k regex:'sweep_rows|update_rows' --csv --log-file $OUT/traffic.csv python tools/traffic_probe.py > $OUT/traffic_probe.log 2>&1
+log "  rc=$? $(wc -l < $OUT/traffic.csv) csv lines"
 fi
 if has launches; then
 log "ncu launch list"

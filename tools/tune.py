@@ -139,16 +139,23 @@ def main():
         good = sorted([r for r in recs if r.get("ok") and "ms_iter" in r], key=lambda r: r["ms_sweep"])
         results[name] = good[:8]
 
-    def S(lpg, block, hint=1, fullrow=0, chunk=256):
-        return dict(lpg=lpg, block=block, hint=hint, fullrow=fullrow, chunk=chunk)
+    def S(lpg, depth, block, minb, hint=2, fullrow=0, chunk=256, **kw):
+        return dict(lpg=lpg, depth=depth, block=block, minb=minb, hint=hint, fullrow=fullrow, chunk=chunk, **kw)
 
-    workload("k50", 50, 4, [96.0, 64.0, 48.0, 128.0, 1e6, 32.0],
-             [S(4, 128), S(8, 256), S(8, 128), S(4, 64), S(4, 128, hint=0), S(8, 256, hint=0), S(4, 128, fullrow=1),
-              S(8, 256, fullrow=1), S(4, 128, chunk=128), S(4, 128, chunk=512), S(8, 256, chunk=512),
-              S(4, 128, chunk=1024)], 0.55)
-    workload("k30", 30, 4, [96.0, 48.0, 1e6], [S(4, 256), S(4, 128), S(8, 256)], 0.7)
-    workload("k128", 128, 4, [96.0, 48.0, 192.0], [S(8, 128), S(16, 256), S(16, 128), S(8, 64)], 0.85)
-    workload("f64", 50, 8, [96.0, 48.0], [S(16, 128), S(8, 128)], 1.0)
+    def G(lpg, depth, block, minb, **kw):   # shared-memory ring, whole-stride copies (the production form)
+        return S(lpg, depth, block, minb, hint=0, fullrow=1, smem_gather=1, **kw)
+
+    def R(lpg, depth, block, minb, **kw):   # register gathers
+        return S(lpg, depth, block, minb, hint=0, fullrow=0, smem_gather=0, **kw)
+
+    workload("k50", 50, 4, [96.0, 64.0],
+             [G(8, 4, 256, 3), G(8, 4, 128, 6), G(8, 2, 256, 4), G(8, 4, 256, 2), R(8, 2, 256, 4)], 0.3)
+    workload("k30", 30, 4, [96.0, 48.0, 1e6],
+             [G(8, 4, 256, 4), G(8, 2, 256, 4), G(4, 4, 256, 3), G(8, 4, 128, 6), R(8, 4, 256, 4), R(4, 4, 256, 3)], 0.55)
+    workload("k128", 128, 4, [96.0, 192.0, 48.0],
+             [G(8, 4, 128, 3), G(16, 4, 256, 3), G(16, 2, 256, 3), G(8, 2, 128, 4), G(8, 4, 128, 2), R(16, 2, 256, 3)], 0.8)
+    workload("f64", 50, 8, [96.0, 48.0, 192.0],
+             [G(8, 4, 128, 3), G(16, 4, 128, 4), G(8, 2, 128, 3), G(16, 2, 128, 4), R(8, 2, 128, 3)], 1.0)
     print("== best ==")
     for name, good in results.items():
         for r in good[:4]:
