@@ -261,13 +261,15 @@ def cpu_reference_rate(a, warm_iters, timed_iters, div):
 
 def run_reference(a):
     """The reference arm: the reference's own CPU implementation, its stock entry point (fit_hpf, pxi:147), all
-    host threads, on the SAME configuration as the GPU arm (unless --ref-sample-div says otherwise): W warm-up
-    iterations in one call, then W+K in a second; ms_per_step = their difference / K."""
+    host threads, on the SAME configuration as the GPU arm (unless --ref-sample-div says otherwise).  One iteration
+    costs ~13 s at the headline size, so the warm-up is ONE call with maxiter=1 (it pays the same initialisation and
+    phi allocation as the timed call, and first-touches the pages); the timed call runs K+1 iterations and
+    ms_per_step = (t[K+1] - t[1]) / K: exactly K timed iterations, all of them executed."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     div = max(1, a.ref_sample_div)
-    res = cpu_reference_rate(a, a.warmup, a.steps, div)
+    res = cpu_reference_rate(a, 1, a.steps, div)
     if res is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built on this box"}))
         return
@@ -449,9 +451,9 @@ def run_ours(a):
                     k_rte=(nUl, 1), t_rte=(nI, 1), Theta=(nUl, k), Beta=(nI, k))
         out_pinned = {key: torch.empty(shape, dtype=tdt).pin_memory() for key, shape in outs.items()}
         out_state = {key: t.numpy() for key, t in out_pinned.items()}
+        eng.close()
         if runner is not None:
             runner.close()
-        eng.close()
         del lu, li, ly, state
         torch.cuda.empty_cache()
         h2d = hu.nbytes + hi_.nbytes + hy.nbytes + sum(x.nbytes for x in hstate)
@@ -481,9 +483,9 @@ def run_ours(a):
             lap()
             e.export_state(**out_state)
             lap()
+            e.close()
             if r is not None:
                 r.close()
-            e.close()
             if legs is not None:
                 for name, j in (("create_ms", 0), ("load_state_ms", 1), ("load_coo_ms", 2), ("iterate_ms", 3), ("export_ms", 4)):
                     legs[name] = round(1e3 * (t[j + 1] - t[j]), 2)
@@ -506,9 +508,9 @@ def run_ours(a):
                        "bytes are per call / iterations, summed over ranks; breakdown from a separate call with a "
                        "device synchronize after every leg" % a.steps}
     else:
+        eng.close()
         if runner is not None:
             runner.close()
-        eng.close()
 
     if rank != 0:
         if world > 1:

@@ -36,6 +36,9 @@ SIGNATURES = {
     "hpf_partials": ([_P, _c.POINTER(_P), _c.POINTER(_I64), _c.POINTER(_P), _c.POINTER(_I64)], _c.c_int),
     "hpf_peer_export": ([_P, _P], _c.c_int),
     "hpf_peer_attach": ([_P, _I32, _I32, _P], _c.c_int),
+    "hpf_item_buffer_bytes": ([_P, _c.POINTER(_I64)], _c.c_int),
+    "hpf_adopt_item_buffers": ([_P, _c.POINTER(_P)], _c.c_int),
+    "hpf_peer_attach_ptrs": ([_P, _I32, _I32, _c.POINTER(_P), _c.POINTER(_P)], _c.c_int),
     "hpf_update_items_peer": ([_P, _I32], _c.c_int),
     "hpf_peer_finish": ([_P], _c.c_int),
     "hpf_beta_colsum": ([_P, _c.POINTER(_P), _c.POINTER(_I64)], _c.c_int),

@@ -280,6 +280,8 @@ struct hpf_engine {
     // multi-GPU peer memory (hpf_peer_attach): every rank's item-side buffers, opened through CUDA IPC
     hpf::PeerTable peers;
     bool peer_attached = false;
+    bool peer_multicast = false;  // peers.mc_* are valid: the exchange kernel uses multimem.ld_reduce / multimem.st
+    bool items_adopted = false;   // the five item-side buffers belong to the caller (symmetric memory): never freed here
     std::vector<void*> ipc_opened;
     // minibatch membership stamps (allocated at the first hpf_step_batch)
     int *stamp_u = nullptr, *stamp_i = nullptr;
@@ -777,6 +779,7 @@ int hpf_destroy(hpf_engine* h) {
         if (h->ep_pin[b]) cudaFreeHost(h->ep_pin[b]);
         if (h->ep_ev[b]) cudaEventDestroy(h->ep_ev[b]);
     }
+    if (h->items_adopted) h->accI = h->xi = h->trte = h->Lshp = h->Lrte = nullptr;
     void* ptrs[] = {h->Gshp, h->Grte, h->Lshp, h->Lrte, h->krte, h->trte, h->xu, h->xi, h->accU, h->accI, h->Tsum, h->Bsum, h->stamp_u, h->stamp_i,
                     h->bt_major, h->bt_minor, h->bt_cnt, h->bt_off, h->bt_ids, h->bt_val, h->bt_scan_tmp, h->dirU, h->dirI, h->ep_ids};
     for (void* p : ptrs) hpf_free(p);
@@ -1125,6 +1128,73 @@ int hpf_peer_attach(hpf_engine* h, int32_t rank, int32_t world, const void* all_
         h->peers.shp[p] = ptr[3];
         h->peers.rte[p] = ptr[4];
     }
+    h->peers.mc_acc = h->peers.mc_x = h->peers.mc_rate = h->peers.mc_shp = h->peers.mc_rte = nullptr;
+    h->peer_multicast = false;
+    h->peers.world = world;
+    h->peers.rank = rank;
+    h->peer_attached = true;
+    return HPF_OK;
+}
+
+int hpf_item_buffer_bytes(hpf_engine* h, int64_t out[HPF_PEER_BUFFERS]) {
+    if (!h || !out) return fail(HPF_EINVAL, "NULL argument");
+    const int64_t mi = (int64_t)h->mat_bytes(h->nI > 0 ? h->nI : 1);
+    out[0] = mi;                                            // item_sums
+    out[1] = mi;                                            // item softmax factors
+    out[2] = (int64_t)(h->nI > 0 ? h->nI : 1) * h->rb;      // t_rte
+    out[3] = mi;                                            // Lambda_shp
+    out[4] = mi;                                            // Lambda_rte
+    return HPF_OK;
+}
+
+int hpf_adopt_item_buffers(hpf_engine* h, void* const bufs[HPF_PEER_BUFFERS]) {
+    if (!h || !bufs) return fail(HPF_EINVAL, "NULL argument");
+    if (h->state_loaded || h->data_loaded) return fail(HPF_ESTATE, "hpf_adopt_item_buffers must precede hpf_load_state / hpf_load_coo");
+    for (int b = 0; b < HPF_PEER_BUFFERS; ++b)
+        if (!bufs[b] || !is_device_ptr(bufs[b]) || ((uintptr_t)bufs[b] & 255u))
+            return fail(HPF_EINVAL, "item buffer %d must be a 256-byte aligned device pointer", b);
+    DeviceGuard guard(h->device);
+    if (!h->items_adopted) {
+        void* mine[] = {h->accI, h->xi, h->trte, h->Lshp, h->Lrte};
+        for (void* p : mine) hpf_free(p);
+    }
+    h->accI = bufs[0];
+    h->xi = bufs[1];
+    h->trte = bufs[2];
+    h->Lshp = bufs[3];
+    h->Lrte = bufs[4];
+    h->items_adopted = true;
+    // same initial contents as hpf_create gives its own buffers: pad packs of the factor buffer defined, sums zero
+    const size_t mi = h->mat_bytes(h->nI > 0 ? h->nI : 1);
+    CK(cudaMemsetAsync(h->xi, 0, mi, h->stream));
+    CK(cudaMemsetAsync(h->accI, 0, mi, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->x_valid = false;
+    return HPF_OK;
+}
+
+int hpf_peer_attach_ptrs(hpf_engine* h, int32_t rank, int32_t world, void* const* peer_ptrs, void* const* mc_ptrs) {
+    if (!h || !peer_ptrs) return fail(HPF_EINVAL, "NULL argument");
+    if (world < 1 || world > hpf::kMaxPeers || rank < 0 || rank >= world)
+        return fail(HPF_EINVAL, "bad rank/world (%d/%d, at most %d peers)", rank, world, hpf::kMaxPeers);
+    void* own[HPF_PEER_BUFFERS] = {h->accI, h->xi, h->trte, h->Lshp, h->Lrte};
+    for (int b = 0; b < HPF_PEER_BUFFERS; ++b)
+        if (peer_ptrs[(size_t)rank * HPF_PEER_BUFFERS + b] != own[b])
+            return fail(HPF_EINVAL, "peer table entry of this rank is not the engine's own buffer %d (adopt the buffers first)", b);
+    for (int p = 0; p < world; ++p) {
+        void* const* row = peer_ptrs + (size_t)p * HPF_PEER_BUFFERS;
+        h->peers.acc[p] = row[0];
+        h->peers.x[p] = row[1];
+        h->peers.rate[p] = row[2];
+        h->peers.shp[p] = row[3];
+        h->peers.rte[p] = row[4];
+    }
+    h->peer_multicast = mc_ptrs != nullptr && mc_ptrs[0] != nullptr;
+    h->peers.mc_acc = h->peer_multicast ? mc_ptrs[0] : nullptr;
+    h->peers.mc_x = h->peer_multicast ? mc_ptrs[1] : nullptr;
+    h->peers.mc_rate = h->peer_multicast ? mc_ptrs[2] : nullptr;
+    h->peers.mc_shp = h->peer_multicast ? mc_ptrs[3] : nullptr;
+    h->peers.mc_rte = h->peer_multicast ? mc_ptrs[4] : nullptr;
     h->peers.world = world;
     h->peers.rank = rank;
     h->peer_attached = true;
@@ -1146,11 +1216,18 @@ int hpf_update_items_peer(hpf_engine* h, int32_t materialize) {
             const int grid = row_grid(r1 - r0, C::lpg);
             const size_t smem = sizeof(double) * h->ld;
             const real prior = (real)h->c, shp_rate = (real)h->t_shp, add_rate = (real)h->add_t;
-            if (materialize)
-                hpf::update_items_peer_kernel<real, C::lpg, C::vpl, true><<<grid, 256, smem, h->stream>>>(
+            if (h->peer_multicast) {
+                if (materialize)
+                    hpf::update_items_peer_kernel<real, C::lpg, C::vpl, true, true><<<grid, 256, smem, h->stream>>>(
+                        r0, r1, h->ld, h->k, h->peers, h->Tsum, h->Bsum, prior, shp_rate, add_rate);
+                else
+                    hpf::update_items_peer_kernel<real, C::lpg, C::vpl, false, true><<<grid, 256, smem, h->stream>>>(
+                        r0, r1, h->ld, h->k, h->peers, h->Tsum, h->Bsum, prior, shp_rate, add_rate);
+            } else if (materialize)
+                hpf::update_items_peer_kernel<real, C::lpg, C::vpl, true, false><<<grid, 256, smem, h->stream>>>(
                     r0, r1, h->ld, h->k, h->peers, h->Tsum, h->Bsum, prior, shp_rate, add_rate);
             else
-                hpf::update_items_peer_kernel<real, C::lpg, C::vpl, false><<<grid, 256, smem, h->stream>>>(
+                hpf::update_items_peer_kernel<real, C::lpg, C::vpl, false, false><<<grid, 256, smem, h->stream>>>(
                     r0, r1, h->ld, h->k, h->peers, h->Tsum, h->Bsum, prior, shp_rate, add_rate);
             h->launches++;
             CKK();

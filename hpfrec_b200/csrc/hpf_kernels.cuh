@@ -134,11 +134,47 @@ struct PeerTable {
     void* rate[kMaxPeers];
     void* shp[kMaxPeers];
     void* rte[kMaxPeers];
+    // NVSwitch multicast views of the same five buffers (NULL without multicast support): one multimem.ld_reduce on
+    // mc_acc returns the sum over every rank's copy, computed inside the switch; a store to mc_x lands in every replica
+    void *mc_acc, *mc_x, *mc_rate, *mc_shp, *mc_rte;
     int world;
     int rank;
 };
 
-template <typename real, int LPG, int VPL, bool MAT>
+// multimem (NVLS) accessors: SASS LDGMC.E.ADD / STG on a multicast address
+__device__ __forceinline__ Pack<float> mc_ld_reduce(const float* p) {
+    Pack<float> r;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3])
+                 : "l"(p)
+                 : "memory");
+    return r;
+}
+__device__ __forceinline__ Pack<double> mc_ld_reduce(const double* p) {
+    Pack<double> r;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f64 %0, [%1];" : "=d"(r.v[0]) : "l"(p) : "memory");
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f64 %0, [%1];" : "=d"(r.v[1]) : "l"(p + 1) : "memory");
+    return r;
+}
+__device__ __forceinline__ void mc_st(float* p, const Pack<float>& r) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]),
+                 "f"(r.v[3])
+                 : "memory");
+}
+__device__ __forceinline__ void mc_st(double* p, const Pack<double>& r) {
+    asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(r.v[0]) : "memory");
+    asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p + 1), "d"(r.v[1]) : "memory");
+}
+__device__ __forceinline__ void mc_st_scalar(float* p, float v) {
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void mc_st_scalar(double* p, double v) {
+    asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+// MC: the reduce-scatter is ONE multimem.ld_reduce per pack (the NVSwitch adds the ranks' copies: this GPU receives
+// 1/world of the bytes the pull form moves) and the all-gather ONE multimem.st per pack.
+template <typename real, int LPG, int VPL, bool MAT, bool MC>
 __global__ void __launch_bounds__(256)
 update_items_peer_kernel(int r0, int r1, int ld, int k, PeerTable pt, const double* __restrict__ colsum_other,
                          double* __restrict__ colsum_out, real prior, real shp_rate, real add_rate) {
@@ -176,7 +212,12 @@ update_items_peer_kernel(int r0, int r1, int ld, int k, PeerTable pt, const doub
         // ~2 us latency, so memory-level parallelism per thread is what fills the links
 #pragma unroll
         for (int v = 0; v < VPL; ++v) asum[v] = pack_zero<real>();
-        for (int p0 = 0; p0 < pt.world; p0 += 8) {
+        if (MC) {
+#pragma unroll
+            for (int v = 0; v < VPL; ++v)
+                if (act[v]) asum[v] = mc_ld_reduce((const real*)pt.mc_acc + (size_t)r * ld + off[v]);
+        }
+        for (int p0 = 0; !MC && p0 < pt.world; p0 += 8) {
             Pack<real> pv[VPL][8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -224,7 +265,14 @@ update_items_peer_kernel(int r0, int r1, int ld, int k, PeerTable pt, const doub
             Pack<real> xn;
 #pragma unroll
             for (int e = 0; e < EPV; ++e) xn.v[e] = (off[v] + e < k) ? rexp(E[v].v[e] - m) : real(0);
-            for (int p = 0; p < pt.world; ++p) {
+            if (MC) {
+                mc_st((real*)pt.mc_x + at, xn);
+                if (MAT) {
+                    mc_st((real*)pt.mc_shp + at, shp[v]);
+                    mc_st((real*)pt.mc_rte + at, rte[v]);
+                }
+            }
+            for (int p = 0; !MC && p < pt.world; ++p) {
                 st_pack((real*)pt.x[p] + at, xn);
                 if (MAT) {
                     st_pack((real*)pt.shp[p] + at, shp[v]);
@@ -232,8 +280,10 @@ update_items_peer_kernel(int r0, int r1, int ld, int k, PeerTable pt, const doub
                 }
             }
         }
-        if (gl == 0)
-            for (int p = 0; p < pt.world; ++p) ((real*)pt.rate[p])[r] = new_rate;
+        if (gl == 0) {
+            if (MC) mc_st_scalar((real*)pt.mc_rate + r, new_rate);
+            for (int p = 0; !MC && p < pt.world; ++p) ((real*)pt.rate[p])[r] = new_rate;
+        }
     }
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {

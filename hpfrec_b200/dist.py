@@ -140,6 +140,33 @@ def attach_peers(engine, group=None):
     engine.peer_attach(rank, world, b"".join(_all_gather_bytes(engine.peer_export(), group)))
 
 
+def attach_symmetric(engine, group=None, multicast=True):
+    """Moves the engine's five item-side buffers into ONE symmetric allocation (torch.distributed._symmetric_memory:
+    every rank allocates the same size, the rendezvous maps every rank's copy into this process and, on NVSwitch
+    systems, also creates a multicast mapping), then hands the peer and multicast pointers to the engine.  Must run
+    before hpf_load_state.  Returns (handle, tensor, used_multicast); keep both alive as long as the engine."""
+    import torch
+    import torch.distributed as dist
+    import torch.distributed._symmetric_memory as symm_mem
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sizes = engine.item_buffer_bytes()
+    offs, total = [], 0
+    for nbytes in sizes:
+        offs.append(total)
+        total += (nbytes + 4095) // 4096 * 4096
+    dev = torch.device("cuda", torch.cuda.current_device())
+    t = symm_mem.empty(total, dtype=torch.uint8, device=dev)
+    hdl = symm_mem.rendezvous(t, group if group is not None else dist.group.WORLD)
+    bases = [int(p) for p in hdl.buffer_ptrs]
+    if bases[rank] != t.data_ptr():
+        raise RuntimeError("symmetric memory: this rank's mapped pointer is not the tensor's own")
+    mc_base = int(getattr(hdl, "multicast_ptr", 0) or 0) if multicast else 0
+    engine.adopt_item_buffers([t.data_ptr() + o for o in offs])
+    peer_ptrs = [[bases[p] + o for o in offs] for p in range(world)]
+    engine.peer_attach_ptrs(rank, world, peer_ptrs, [mc_base + o for o in offs] if mc_base else None)
+    return hdl, t, bool(mc_base)
+
+
 def run_sharded_iterations_peer(engine, niter, group=None, materialize_last=True):
     """User-sharded iterations with the item-side exchange fused into ONE kernel over NVLink peer
     memory (hpf_update_items_peer): each rank reduces its slice of item rows straight out of the other
@@ -169,11 +196,15 @@ class ShardedLoop:
     iteration as a CUDA graph (kernels + collectives) so that the per-iteration host cost is a single graph
     launch instead of ~9 Python -> C / c10d calls.
 
-    mode: "peer"    fused reduce-scatter + item update + all-gather kernel over NVLink peer memory (CUDA IPC)
+    mode: "nvls"    fused reduce-scatter + item update + all-gather kernel over NVSwitch multicast memory:
+                    multimem.ld_reduce sums every rank's partial sums inside the switch, multimem.st broadcasts
+                    the updated rows (symmetric memory; falls back to "symm" when the system has no multicast)
+          "symm"    the same kernel with peer loads / stores over symmetric memory
+          "peer"    the same kernel over CUDA-IPC mapped buffers
           "overlap" NCCL all-reduce of the item-side partial sums, overlapping the user-major pass
           "plain"   NCCL all-reduce after both passes
-          "auto"    "peer"
-    Construct it BEFORE hpf_load_state (the peer mode maps the engine's item-side buffers into every rank)."""
+          "auto"    "nvls" with NCCL, else "peer"
+    Construct it BEFORE hpf_load_state (the fused modes map the engine's item-side buffers into every rank)."""
 
     def __init__(self, engine, mode="auto", group=None, graph=False):
         import torch
@@ -181,11 +212,21 @@ class ShardedLoop:
         self.engine, self.group = engine, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         if mode == "auto":
-            mode = "peer"
+            mode = "nvls" if (dist.is_initialized() and dist.get_backend(group) == "nccl") else "peer"
         if self.world == 1:
             mode = "single"
-        if mode not in ("peer", "overlap", "plain", "single"):
+        if mode not in ("nvls", "symm", "peer", "overlap", "plain", "single"):
             raise ValueError("unknown exchange mode %r" % (mode,))
+        self._symm = None
+        if mode in ("nvls", "symm"):
+            try:
+                hdl, t, used_mc = attach_symmetric(engine, group, multicast=(mode == "nvls"))
+                self._symm = (hdl, t)
+                mode = "nvls" if used_mc else "symm"
+            except Exception as exc:   # no symmetric-memory support on this system: CUDA IPC does the same job
+                import warnings
+                warnings.warn("symmetric memory unavailable (%r): using the CUDA-IPC peer exchange" % (exc,))
+                mode = "peer"
         self.mode = mode
         self.use_graph = bool(graph) and self.world > 1
         self.stream = torch.cuda.Stream() if self.use_graph else torch.cuda.current_stream()
@@ -202,7 +243,7 @@ class ShardedLoop:
     def _iterations(self, n, materialize_last):
         if self.mode == "single":
             self.engine.step_full(n)
-        elif self.mode == "peer":
+        elif self.mode in ("peer", "nvls", "symm"):
             run_sharded_iterations_peer(self.engine, n, self.group, materialize_last=materialize_last)
         elif self.mode == "overlap":
             run_sharded_iterations_overlapped(self.engine, n, group=self.group)
@@ -239,7 +280,9 @@ class ShardedLoop:
         cur.wait_stream(self.stream)
 
     def close(self):
+        """Call AFTER the engine is closed when symmetric memory is in use (the engine's item buffers live in it)."""
         self.graph = None
+        self._symm = None
 
 
 def sharded_parity_check(local_device, options=None, nU=60_000, nI=25_000, nnz=1_500_000, k=50, its=3, mode=None,
@@ -273,8 +316,8 @@ def sharded_parity_check(local_device, options=None, nU=60_000, nI=25_000, nnz=1
     loop.run(its)
     torch.cuda.synchronize()
     mine = eng.export_all()
-    loop.close()
     eng.close()
+    loop.close()
     cdev = dev if dist.get_backend(group) == "nccl" else torch.device("cpu")
     beta = torch.from_numpy(mine["Beta"]).to(cdev)
     ref_beta = beta.clone()

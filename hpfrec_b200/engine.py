@@ -193,6 +193,27 @@ class Engine:
         buf = ctypes.create_string_buffer(bytes(all_handles), len(all_handles))
         _lib.check(self._lib.hpf_peer_attach(self._h, int(rank), int(world), ctypes.cast(buf, ctypes.c_void_p)))
 
+    N_PEER_BUFFERS = 5
+
+    def item_buffer_bytes(self):
+        """Sizes of the five item-side buffers (item sums, item factors, t_rte, Lambda_shp, Lambda_rte)."""
+        out = (ctypes.c_int64 * self.N_PEER_BUFFERS)()
+        _lib.check(self._lib.hpf_item_buffer_bytes(self._h, out))
+        return list(out)
+
+    def adopt_item_buffers(self, ptrs):
+        """Use caller-owned device memory (e.g. symmetric memory) for the five item-side buffers."""
+        arr = (ctypes.c_void_p * self.N_PEER_BUFFERS)(*[int(p) for p in ptrs])
+        _lib.check(self._lib.hpf_adopt_item_buffers(self._h, arr))
+
+    def peer_attach_ptrs(self, rank, world, peer_ptrs, mc_ptrs=None):
+        """peer_ptrs[p][b]: rank p's buffer b as mapped in THIS process; mc_ptrs[b]: multicast mapping or None."""
+        flat = (ctypes.c_void_p * (world * self.N_PEER_BUFFERS))(*[int(x) for row in peer_ptrs for x in row])
+        mc = None
+        if mc_ptrs is not None:
+            mc = (ctypes.c_void_p * self.N_PEER_BUFFERS)(*[int(x) for x in mc_ptrs])
+        _lib.check(self._lib.hpf_peer_attach_ptrs(self._h, int(rank), int(world), flat, mc))
+
     def update_items_peer(self, materialize=True):
         _lib.check(self._lib.hpf_update_items_peer(self._h, int(bool(materialize))))
 

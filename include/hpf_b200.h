@@ -131,6 +131,16 @@ int hpf_partials(hpf_engine* h, void** item_sums, int64_t* item_sums_count, void
 #define HPF_PEER_BUFFERS 5
 int hpf_peer_export(hpf_engine* h, void* handles);
 int hpf_peer_attach(hpf_engine* h, int32_t rank, int32_t world, const void* all_handles);
+/* The same exchange over caller-provided SYMMETRIC memory (every rank allocates the five item-side buffers at the
+ * same offsets of one symmetric allocation, e.g. torch.distributed._symmetric_memory, which also yields an NVSwitch
+ * multicast mapping of it): hpf_item_buffer_bytes gives the sizes, hpf_adopt_item_buffers makes the engine use the
+ * caller's buffers (before hpf_load_state; never freed by the engine), hpf_peer_attach_ptrs takes the [world][5] table
+ * of unicast peer pointers and, optionally, the five multicast pointers.  With multicast pointers the kernel of
+ * hpf_update_items_peer reduces with multimem.ld_reduce (the switch sums the ranks' copies) and broadcasts with
+ * multimem.st; without them it uses the peer loads / stores above. */
+int hpf_item_buffer_bytes(hpf_engine* h, int64_t out[HPF_PEER_BUFFERS]);
+int hpf_adopt_item_buffers(hpf_engine* h, void* const bufs[HPF_PEER_BUFFERS]);
+int hpf_peer_attach_ptrs(hpf_engine* h, int32_t rank, int32_t world, void* const* peer_ptrs, void* const* mc_ptrs);
 int hpf_update_items_peer(hpf_engine* h, int32_t materialize);
 int hpf_peer_finish(hpf_engine* h);
 int hpf_beta_colsum(hpf_engine* h, void** ptr, int64_t* count);

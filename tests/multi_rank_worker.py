@@ -27,9 +27,9 @@ def main():
     else:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    modes = os.environ.get("HPF_TEST_MODES", "peer,overlap,plain").split(",")
+    modes = os.environ.get("HPF_TEST_MODES", "peer,overlap,plain" if shared else "nvls,symm,peer,overlap,plain").split(",")
     for mode in modes:
-        for graph in ((False, True) if (not shared and mode == "peer") else (False,)):
+        for graph in ((False, True) if (not shared and mode in ("peer", "nvls")) else (False,)):
             try:
                 res = hdist.sharded_parity_check(local, nU=20_000, nI=8_000, nnz=400_000, k=50, its=3, mode=mode, graph=graph)
             except Exception as exc:  # a failed check must fail the test, not hang the other ranks

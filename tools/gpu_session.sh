@@ -15,7 +15,7 @@ python -c "import os; print('cpus', len(os.sched_getaffinity(0)))" > $OUT/host.t
 
 if has test; then
 log "parity tests"
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_refscale.py tests/test_gpu_api.py -m gpu -q > $OUT/pytest_parity.log 2>&1
+timeout 900 python -m pytest tests -m gpu -q ${PYTEST_ARGS:-} > $OUT/pytest_parity.log 2>&1
 log "  rc=$? $(tail -1 $OUT/pytest_parity.log)"
 fi
 if has tune; then
@@ -59,6 +59,23 @@ if has bench; then
 log "bench"
 timeout 400 python bench.py --steps 20 --warmup 3 ${BENCH_ARGS:-} > $OUT/bench.json 2> $OUT/bench.err
 log "  rc=$? $(cut -c1-200 $OUT/bench.json)"
+fi
+if has c4; then
+log "bench --config C4 (SVI epochs)"
+timeout 300 python bench.py --config C4 --steps 8 --warmup 4 > $OUT/bench_C4.json 2> $OUT/bench_C4.err
+log "  rc=$? $(cut -c1-200 $OUT/bench_C4.json)"
+fi
+if has configs; then
+for CFG in C2 C3 H_f64; do
+log "bench --config $CFG"
+timeout 300 python bench.py --config $CFG --steps 20 --warmup 3 --no-cpu-baseline > $OUT/bench_$CFG.json 2> $OUT/bench_$CFG.err
+log "  rc=$? $(cut -c1-200 $OUT/bench_$CFG.json)"
+done
+fi
+if has refarm; then
+log "bench --impl reference (full configuration, ${REF_STEPS:-3} steps)"
+timeout 900 python bench.py --impl reference --steps ${REF_STEPS:-3} --warmup ${REF_WARMUP:-1} > $OUT/bench_reference.json 2> $OUT/bench_reference.err
+log "  rc=$? $(cut -c1-300 $OUT/bench_reference.json)"
 fi
 if has fullsize; then
 log "full-size invariants"
