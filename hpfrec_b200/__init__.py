@@ -157,6 +157,11 @@ class HPF:
         self.step_size = step_size
         self.allow_inconsistent_math = bool(allow_inconsistent_math)
         self.use_float = bool(use_float)
+        # engine limit (the reference has none): a factor row must fit the widest lane-group shape, 128 packs of 16 bytes
+        kmax = 512 if self.use_float else 256
+        if self.k > kmax:
+            raise ValueError("k=%d exceeds what the CUDA engine supports for %s (k <= %d)"
+                             % (self.k, "float32" if self.use_float else "float64", kmax))
         self.random_seed = random_seed
         self.stop_crit = stop_crit
         self.reindex = bool(reindex)
@@ -807,3 +812,10 @@ class HPF:
         print("Number of items: %d" % self.nitems)
         print("Latent factors to use: %d" % self.k)
         print("")
+
+
+def trim_cache():
+    """Returns the device blocks the engine's allocator keeps cached between fits to the CUDA driver."""
+    from . import _lib
+    _lib.check(_lib.load().hpf_trim_cache())
+

@@ -292,23 +292,26 @@ __global__ void batch_count_kernel(int n_ids, const int* __restrict__ ids, const
 template <typename real>
 __global__ void __launch_bounds__(256)
 batch_expand_kernel(int n_ids, const int* __restrict__ ids, const int* __restrict__ ptr,
-                    const int* __restrict__ off, const int* __restrict__ src_minor,
+                    const int* __restrict__ off, long long total, const int* __restrict__ src_minor,
                     const real* __restrict__ src_val, int* __restrict__ out_major, int* __restrict__ out_minor,
                     real* __restrict__ out_val, int* __restrict__ stamp_minor, int step) {
-    // one warp per listed row: coalesced copy of its CSR/CSC segment
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int q = warp; q < n_ids; q += nwarps) {
-        const int id = ids[q];
-        const int beg = ptr[id], len = ptr[id + 1] - beg, dst = off[q];
-        for (int t = lane; t < len; t += 32) {
-            const int m = src_minor[beg + t];
-            out_major[dst + t] = id;
-            out_minor[dst + t] = m;
-            out_val[dst + t] = src_val[beg + t];
-            stamp_minor[m] = step;  // benign race: every writer stores the same value
-        }
+    // one thread per OUTPUT triple (balanced whatever the row degrees: an item batch holds rows of 10^5 nnz next to
+    // rows of one): binary search of the position in the exclusive offsets gives the listed row it belongs to
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    int lo = 0, hi = n_ids;  // off[lo] <= t < off[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(off + mid) <= (int)t) lo = mid;
+        else hi = mid;
     }
+    const int id = __ldg(ids + lo);
+    const int src = __ldg(ptr + id) + ((int)t - __ldg(off + lo));
+    const int m = __ldg(src_minor + src);
+    out_major[t] = id;
+    out_minor[t] = m;
+    out_val[t] = __ldg(src_val + src);
+    stamp_minor[m] = step;  // benign race: every writer stores the same value
 }
 
 // row pointer array of a sorted ordering: ptr[r] = first position with row >= r

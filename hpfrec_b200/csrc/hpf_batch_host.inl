@@ -23,7 +23,7 @@ int ensure_stamps(hpf_engine* h) {
 // given and rates are blended on batch rows only; otherwise all rows are walked under the stamp.
 int batch_core(hpf_engine* h, const int* iu, const int* ii, const void* yv, int64_t nnz, const int* list_major,
                int64_t n_major_ids, const int* list_minor, int64_t n_minor_ids, bool user_batch, double rho,
-               double mult, bool blend_all, int step) {
+               double mult, bool blend_all, int step, bool grouped_padded = false) {
     h->x_valid = false;  // per-row factors / accumulators are only valid for the batch rows from here on
     drop_graphs(h);
     TRY(resolve_robust(h));
@@ -62,8 +62,12 @@ int batch_core(hpf_engine* h, const int* iu, const int* ii, const void* yv, int6
             h->launches++;
         }
         CKK();
-        // 2. phi + scatter over the batch triples (update_phi + update_G_n_L_sh)
-        TRY(launch_sweep_coo<C>(h, iu, ii, yv, nnz, h->xu, h->xi, h->accU, h->accI, ld, nullptr, k, h->stream));
+        // 2. phi + scatter over the batch triples (update_phi + update_G_n_L_sh).  Device-assembled batches are grouped
+        //    by the batched side and padded: their batched side accumulates in registers (one RED per row, not per nnz)
+        if (grouped_padded && !h->robust_on)
+            TRY(launch_sweep_batch<C>(h, ub ? iu : ii, ub ? ii : iu, yv, nnz, xM, xm, accM, accm));
+        else
+            TRY(launch_sweep_coo<C>(h, iu, ii, yv, nnz, h->xu, h->xi, h->accU, h->accI, ld, nullptr, k, h->stream));
         // 3. column sums of the minor side's current expectation (Beta.sum(0) at pxi:300, Theta.sum(0) at 352).
         //    Between consecutive minibatch steps they are carried: the major kernel recomputes its side's sums in
         //    full, the minor kernel adds the change of its batch rows (in double), so only the first step after
@@ -241,28 +245,28 @@ extern "C" int hpf_step_batch_ids(hpf_engine* h, const void* ids, int64_t n_ids,
     // compact triples of the batch (row after row, like get_i_batch_pass2) + stamps of the minor ids
     if (total > h->bt_cap_nnz || !h->bt_major) {
         int64_t c1 = 0, c2 = 0, c3 = 0;
-        TRY(grow_bytes((void**)&h->bt_major, &c1, total, sizeof(int)));
-        TRY(grow_bytes((void**)&h->bt_minor, &c2, total, sizeof(int)));
-        TRY(grow_bytes(&h->bt_val, &c3, total, (size_t)h->rb));
-        h->bt_cap_nnz = c1;
+        TRY(grow_bytes((void**)&h->bt_major, &c1, total + kPadEntries, sizeof(int)));
+        TRY(grow_bytes((void**)&h->bt_minor, &c2, total + kPadEntries, sizeof(int)));
+        TRY(grow_bytes(&h->bt_val, &c3, total + kPadEntries, (size_t)h->rb));
+        h->bt_cap_nnz = c1 - kPadEntries;
     }
     if (total > 0) {
-        long long want = ((long long)n_ids * 32 + 255) / 256;
-        if (want > 148 * 16) want = 148 * 16;
         if (h->rb == 4)
-            hpf::batch_expand_kernel<float><<<(unsigned)want, 256, 0, h->stream>>>(
-                (int)n_ids, h->bt_ids, ptr, h->bt_off, src_minor, (const float*)src_val, h->bt_major, h->bt_minor,
+            hpf::batch_expand_kernel<float><<<nblk(total), 256, 0, h->stream>>>(
+                (int)n_ids, h->bt_ids, ptr, h->bt_off, total, src_minor, (const float*)src_val, h->bt_major, h->bt_minor,
                 (float*)h->bt_val, stamp_minor, step);
         else
-            hpf::batch_expand_kernel<double><<<(unsigned)want, 256, 0, h->stream>>>(
-                (int)n_ids, h->bt_ids, ptr, h->bt_off, src_minor, (const double*)src_val, h->bt_major, h->bt_minor,
+            hpf::batch_expand_kernel<double><<<nblk(total), 256, 0, h->stream>>>(
+                (int)n_ids, h->bt_ids, ptr, h->bt_off, total, src_minor, (const double*)src_val, h->bt_major, h->bt_minor,
                 (double*)h->bt_val, stamp_minor, step);
-        h->launches++;
+        if (h->rb == 4) hpf::pad_order_kernel<float><<<nblk(kPadEntries), 256, 0, h->stream>>>(h->bt_major, h->bt_minor, (float*)h->bt_val, total, kPadEntries);
+        else hpf::pad_order_kernel<double><<<nblk(kPadEntries), 256, 0, h->stream>>>(h->bt_major, h->bt_minor, (double*)h->bt_val, total, kPadEntries);
+        h->launches += 2;
         CKK();
     }
     const int* iu = ub ? h->bt_major : h->bt_minor;
     const int* ii = ub ? h->bt_minor : h->bt_major;
-    return batch_core(h, iu, ii, h->bt_val, total, h->bt_ids, n_ids, nullptr, 0, ub, rho, mult, blend_all_rates != 0, step);
+    return batch_core(h, iu, ii, h->bt_val, total, h->bt_ids, n_ids, nullptr, 0, ub, rho, mult, blend_all_rates != 0, step, true);
 }
 
 
@@ -361,10 +365,10 @@ extern "C" int hpf_step_epoch_ids(hpf_engine* h, const void* ids, int64_t n_ids,
     }
     if (max_total > h->bt_cap_nnz || !h->bt_major) {
         int64_t c1 = 0, c2 = 0, c3 = 0;
-        TRY(grow_bytes((void**)&h->bt_major, &c1, max_total, sizeof(int)));
-        TRY(grow_bytes((void**)&h->bt_minor, &c2, max_total, sizeof(int)));
-        TRY(grow_bytes(&h->bt_val, &c3, max_total, (size_t)h->rb));
-        h->bt_cap_nnz = c1;
+        TRY(grow_bytes((void**)&h->bt_major, &c1, max_total + kPadEntries, sizeof(int)));
+        TRY(grow_bytes((void**)&h->bt_minor, &c2, max_total + kPadEntries, sizeof(int)));
+        TRY(grow_bytes(&h->bt_val, &c3, max_total + kPadEntries, (size_t)h->rb));
+        h->bt_cap_nnz = c1 - kPadEntries;
     }
     size_t need = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, need, h->bt_cnt, h->bt_off, (int)rows_cap + 1, h->stream);
@@ -395,23 +399,23 @@ extern "C" int hpf_step_epoch_ids(hpf_engine* h, const void* ids, int64_t n_ids,
         cub::DeviceScan::ExclusiveSum(h->bt_scan_tmp, bytes, h->bt_cnt, h->bt_off, (int)nq + 1, h->stream);
         h->launches += 2;
         if (total > 0) {
-            long long want = ((long long)nq * 32 + 255) / 256;
-            if (want > 148 * 16) want = 148 * 16;
             if (h->rb == 4)
-                hpf::batch_expand_kernel<float><<<(unsigned)want, 256, 0, h->stream>>>(
-                    (int)nq, d_ids, ptr, h->bt_off, src_minor, (const float*)src_val, h->bt_major, h->bt_minor,
+                hpf::batch_expand_kernel<float><<<nblk(total), 256, 0, h->stream>>>(
+                    (int)nq, d_ids, ptr, h->bt_off, total, src_minor, (const float*)src_val, h->bt_major, h->bt_minor,
                     (float*)h->bt_val, stamp_minor, step);
             else
-                hpf::batch_expand_kernel<double><<<(unsigned)want, 256, 0, h->stream>>>(
-                    (int)nq, d_ids, ptr, h->bt_off, src_minor, (const double*)src_val, h->bt_major, h->bt_minor,
+                hpf::batch_expand_kernel<double><<<nblk(total), 256, 0, h->stream>>>(
+                    (int)nq, d_ids, ptr, h->bt_off, total, src_minor, (const double*)src_val, h->bt_major, h->bt_minor,
                     (double*)h->bt_val, stamp_minor, step);
-            h->launches++;
+            if (h->rb == 4) hpf::pad_order_kernel<float><<<nblk(kPadEntries), 256, 0, h->stream>>>(h->bt_major, h->bt_minor, (float*)h->bt_val, total, kPadEntries);
+            else hpf::pad_order_kernel<double><<<nblk(kPadEntries), 256, 0, h->stream>>>(h->bt_major, h->bt_minor, (double*)h->bt_val, total, kPadEntries);
+            h->launches += 2;
         }
         CKK();
         const int* iu = ub ? h->bt_major : h->bt_minor;
         const int* ii = ub ? h->bt_minor : h->bt_major;
         const double mult = (double)n_major / (double)nq;
-        TRY(batch_core(h, iu, ii, h->bt_val, total, d_ids, nq, nullptr, 0, ub, rho, mult, false, step));
+        TRY(batch_core(h, iu, ii, h->bt_val, total, d_ids, nq, nullptr, 0, ub, rho, mult, false, step, true));
     }
     return HPF_OK;
 }

@@ -234,8 +234,8 @@ __device__ __forceinline__ double rdiv_rcp(double a, double b) { return a / b; }
 // digamma for x > 0.  The reference calls scipy.special.cython_special.psi (pxi:5, call sites
 // pxi:570/588/685/717), i.e. cephes `psi`: upward recurrence psi(x) = psi(x+1) - 1/x until x >= 10,
 // then the asymptotic series log(x) - 1/(2x) - sum_n B_2n / (2n x^2n).  Same scheme here (7 Bernoulli
-// terms in double; in float the shift target is 6 and 3 terms already reach 1 ulp).  Validated
-// against scipy on a dense grid in tests/test_digamma.py.
+// terms in double).  Validated against scipy on a dense grid in
+// tests/test_gpu_parity.py::test_digamma_vs_scipy.
 __device__ __forceinline__ double digamma(double x) {
     double acc = 0.0;
     while (x < 10.0) {

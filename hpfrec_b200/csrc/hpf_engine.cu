@@ -129,8 +129,9 @@ inline unsigned nblk(long long n, int t = 256) { return (unsigned)((n + t - 1) /
 // Caching device allocator.  cudaMalloc / cudaFree of the engine's multi-hundred-MB buffers cost tens
 // of milliseconds per fit (cudaFree also synchronises the device); repeated fits in one process
 // (hyper-parameter sweeps, partial_fit loops, the bench's end-to-end call) reuse blocks instead.
-// Blocks are matched by exact (device, rounded size); the cache is capped (HPF_CACHE_MB, default
-// 32768) and can be released with hpf_trim_cache().  All frees in this file happen after the stream
+// Blocks are matched by exact (device, rounded size); the cache is capped (HPF_CACHE_MB, default a
+// quarter of the device's memory) and can be released with hpf_trim_cache().  Buffers that were exported
+// over CUDA IPC are never cached (a remote rank may still have them mapped): hpf_uncached_free.  All frees in this file happen after the stream
 // that used the block has been synchronised, so immediate reuse is safe.
 // -------------------------------------------------------------------------------------------------
 struct DevCache {
@@ -184,14 +185,30 @@ cudaError_t hpf_malloc(T** p, size_t bytes) {
     return hpf_malloc_impl((void**)p, bytes);
 }
 
+// frees a block without offering it to the cache (IPC-exported buffers)
+void hpf_uncached_free(void* p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(g_cache.mu);
+        g_cache.live.erase(p);
+    }
+    cudaFree(p);
+}
+
 void hpf_free(void* p) {
     if (!p) return;
     std::pair<int, size_t> info;
     {
         std::lock_guard<std::mutex> lk(g_cache.mu);
         if (!g_cache.cap_init) {
-            const char* env = getenv("HPF_CACHE_MB");
-            g_cache.cap_bytes = (size_t)(env ? atof(env) : 32768.0) * 1048576ull;
+            // default cap: a quarter of the device's memory (HPF_CACHE_MB overrides); everything beyond it goes
+            // straight back to the driver, so other allocators in the process are never starved by idle blocks
+            size_t free_b = 0, total_b = 0;
+            double cap_mb = 8192.0;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) cap_mb = (double)total_b / 1048576.0 / 4.0;
+            else cudaGetLastError();
+            if (const char* env = getenv("HPF_CACHE_MB")) cap_mb = atof(env);
+            g_cache.cap_bytes = (size_t)cap_mb * 1048576ull;
             g_cache.cap_init = true;
         }
         auto it = g_cache.live.find(p);
@@ -281,6 +298,7 @@ struct hpf_engine {
     hpf::PeerTable peers;
     bool peer_attached = false;
     bool peer_multicast = false;  // peers.mc_* are valid: the exchange kernel uses multimem.ld_reduce / multimem.st
+    bool ipc_exported = false;    // the item-side buffers were handed out with hpf_peer_export
     bool items_adopted = false;   // the five item-side buffers belong to the caller (symmetric memory): never freed here
     std::vector<void*> ipc_opened;
     // minibatch membership stamps (allocated at the first hpf_step_batch)
@@ -780,6 +798,11 @@ int hpf_destroy(hpf_engine* h) {
         if (h->ep_ev[b]) cudaEventDestroy(h->ep_ev[b]);
     }
     if (h->items_adopted) h->accI = h->xi = h->trte = h->Lshp = h->Lrte = nullptr;
+    if (h->ipc_exported) {  // another process may still map these: give them back to the driver, not to the cache
+        void* shared[] = {h->accI, h->xi, h->trte, h->Lshp, h->Lrte};
+        for (void* p : shared) hpf_uncached_free(p);
+        h->accI = h->xi = h->trte = h->Lshp = h->Lrte = nullptr;
+    }
     void* ptrs[] = {h->Gshp, h->Grte, h->Lshp, h->Lrte, h->krte, h->trte, h->xu, h->xi, h->accU, h->accI, h->Tsum, h->Bsum, h->stamp_u, h->stamp_i,
                     h->bt_major, h->bt_minor, h->bt_cnt, h->bt_off, h->bt_ids, h->bt_val, h->bt_scan_tmp, h->dirU, h->dirI, h->ep_ids};
     for (void* p : ptrs) hpf_free(p);
@@ -1097,6 +1120,7 @@ int hpf_peer_export(hpf_engine* h, void* handles) {
     void* bufs[HPF_PEER_BUFFERS] = {h->accI, h->xi, h->trte, h->Lshp, h->Lrte};
     for (int b = 0; b < HPF_PEER_BUFFERS; ++b)
         CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)((char*)handles + (size_t)b * HPF_IPC_HANDLE_BYTES), bufs[b]));
+    h->ipc_exported = true;
     return HPF_OK;
 }
 
@@ -1241,6 +1265,8 @@ int hpf_update_items_peer(hpf_engine* h, int32_t materialize) {
 int hpf_peer_finish(hpf_engine* h) {
     if (!h) return fail(HPF_EINVAL, "engine is NULL");
     DeviceGuard guard(h->device);
+    // (re-zeroing the owned rows in every replica with multicast stores from the exchange kernel was measured:
+    // correct, but slower than this local memset at 2 GPUs and no faster at 8)
     CK(cudaMemsetAsync(h->accI, 0, h->mat_bytes(h->nI), h->stream));
     return HPF_OK;
 }

@@ -226,11 +226,16 @@ __device__ __noinline__ void stage_own_row(uint32_t dst, const char* src, uint32
 // SG:      1 = the gathered rows are staged in a shared-memory ring of D slots with cp.async (LDGSTS: no registers
 //          and no scoreboard per row in flight, but every gathered byte then crosses shared memory twice);
 //          0 = 128-bit loads straight into registers.
-template <typename real, int LPG, int VPL, int D, int MINB, int BLOCK, int HINT, bool FULLROW, bool ROBUST, int PF = 0, int SG = 0>
+// FUSE:    1 = one-pass form for minibatches (triples grouped by the batched side): the walk also pushes
+//          w_n * xown[r, :] into the OTHER side's sums (acc_minor) with one vector RED per pack per nnz, so both
+//          shape matrices come out of one launch (update_phi_csr + update_G_n_L_sh_csr, pxi:666-768).
+template <typename real, int LPG, int VPL, int D, int MINB, int BLOCK, int HINT, bool FULLROW, bool ROBUST, int PF = 0, int SG = 0,
+          int FUSE = 0>
 __global__ void __launch_bounds__(BLOCK, MINB)
 sweep_rows_kernel(const int* __restrict__ row, const int* __restrict__ col, const real* __restrict__ val,
                   long long ngroups, int chunk, const real* __restrict__ xown, const real* __restrict__ xgat,
-                  real* __restrict__ acc, int ld, int kw, float keep_frac, RescueArgs<real> rescue) {
+                  real* __restrict__ acc, int ld, int kw, float keep_frac, RescueArgs<real> rescue,
+                  real* __restrict__ acc_minor) {
     constexpr int EPV = Pack<real>::N;
     constexpr int NG = 32 / LPG;  // lane groups per warp
     using SM = SweepSmem<VPL, SG ? D : 0>;
@@ -412,6 +417,18 @@ sweep_rows_kernel(const int* __restrict__ row, const int* __restrict__ col, cons
             }
 #pragma unroll
             for (int v = 0; v < VPL; ++v) axpy_pack(sum[v], w, gv[v]);
+            if (FUSE) {
+                int rf, cf;
+                lds64(tb_cur ^ ((uint32_t)t * 16u), rf, cf);
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) {
+                    if (!act[v]) continue;
+                    Pack<real> p;
+#pragma unroll
+                    for (int e = 0; e < EPV; ++e) p.v[e] = w * own[v].v[e];
+                    red_add_pack(acc_minor + (size_t)cf * ld + (gl + LPG * v) * EPV, p);
+                }
+            }
             // ---- put step t + D in flight (this batch or the next one), into the registers just consumed
             if (t + D < LPG) stage(t + D, tb_cur ^ ((uint32_t)(t + D) * 16u));
             else stage(t + D, tb_nxt ^ ((uint32_t)(t + D - LPG) * 16u));

@@ -27,7 +27,8 @@ int launch_sweep_rows(hpf_engine* h, const int* row, const int* col, const void*
     const long long warps = groups / (32 / LPG);
     const unsigned grid = (unsigned)((warps + BLOCK / 32 - 1) / (BLOCK / 32));
     kern<<<grid, BLOCK, smem, h->stream>>>(row, col, (const real*)val, groups, h->chunk, (const real*)xown,
-                                           (const real*)xgat, (real*)acc, h->ld, h->kw, (float)h->keep_frac, rescue);
+                                           (const real*)xgat, (real*)acc, h->ld, h->kw, (float)h->keep_frac, rescue,
+                                           (real*)nullptr);
     h->launches++;
     CKK();
     return HPF_OK;
@@ -138,3 +139,31 @@ int launch_sweep_major(hpf_engine* h, const int* row, const int* col, const void
     return launch_sweep_rows_flags<real, C::lpg, C::vpl, 2, 2, 128, false>(h, row, col, val, xown, xgat, acc, rescue, hint,
                                                                           fullrow, smem_gather, robust);
 }
+
+// One-pass sweep of a device-assembled minibatch (triples grouped by the batched side, padded like an ordering):
+// the batched side accumulates in registers per row, the other side takes one vector RED per pack per nnz.
+template <typename C>
+int launch_sweep_batch(hpf_engine* h, const int* major, const int* minor, const void* val, int64_t n, const void* xmajor,
+                       const void* xminor, void* acc_major, void* acc_minor) {
+    using real = typename C::real;
+    if (n == 0) return HPF_OK;
+    constexpr int BLOCK = 128, D = 2, MINB = 2;
+    auto kern = hpf::sweep_rows_kernel<real, C::lpg, C::vpl, D, MINB, BLOCK, 0, false, false, 0, 0, 1>;
+    constexpr int smem = (BLOCK / 32) * (int)hpf::SweepSmem<C::vpl, 0>::WARP;
+    static thread_local bool configured[64] = {};
+    if (h->device >= 64 || !configured[h->device]) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (h->device < 64) configured[h->device] = true;
+    }
+    const int chunk = 64;
+    const long long groups = padded_groups(n, chunk, C::lpg);
+    const long long warps = groups / (32 / C::lpg);
+    const unsigned grid = (unsigned)((warps + BLOCK / 32 - 1) / (BLOCK / 32));
+    kern<<<grid, BLOCK, smem, h->stream>>>(major, minor, (const real*)val, groups, chunk, (const real*)xmajor,
+                                           (const real*)xminor, (real*)acc_major, h->ld, h->kw, 0.f, hpf::RescueArgs<real>{},
+                                           (real*)acc_minor);
+    h->launches++;
+    CKK();
+    return HPF_OK;
+}
+

@@ -65,6 +65,17 @@ log "bench --config C4 (SVI epochs)"
 timeout 300 python bench.py --config C4 --steps 8 --warmup 4 > $OUT/bench_C4.json 2> $OUT/bench_C4.err
 log "  rc=$? $(cut -c1-200 $OUT/bench_C4.json)"
 fi
+if has c5smoke; then
+log "bench --config C5 on ONE GPU (plumbing check of the 500M-nnz path)"
+timeout 600 python bench.py --config C5 --steps 3 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/bench_C5_N1.json 2> $OUT/bench_C5_N1.err
+log "  rc=$? $(cut -c1-300 $OUT/bench_C5_N1.json)"
+fi
+if has c4launches; then
+log "ncu launch list of two SVI epochs"
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $OUT/launches_C4.csv \
+    python bench.py --config C4 --steps 2 --warmup 3 > $OUT/launches_C4.log 2>&1
+log "  rc=$?"
+fi
 if has configs; then
 for CFG in C2 C3 H_f64; do
 log "bench --config $CFG"
