@@ -72,8 +72,8 @@ log "  rc=$? $(cut -c1-300 $OUT/bench_C5_N1.json)"
 fi
 if has c4launches; then
 log "ncu launch list of two SVI epochs"
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $OUT/launches_C4.csv \
-    python bench.py --config C4 --steps 2 --warmup 3 > $OUT/launches_C4.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $OUT/launches_C4.csv \
+    python bench.py --config C4 --steps 2 --warmup 2 --no-e2e --no-cpu-baseline > $OUT/launches_C4.log 2>&1
 log "  rc=$?"
 fi
 if has configs; then
