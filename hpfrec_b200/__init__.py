@@ -289,8 +289,8 @@ class HPF:
         self.input_df = frame
 
         if self.reindex:
-            frame["UserId"], umap = pd.factorize(frame["UserId"])
-            frame["ItemId"], imap = pd.factorize(frame["ItemId"])
+            frame["UserId"], umap = self._factorize(frame["UserId"])
+            frame["ItemId"], imap = self._factorize(frame["ItemId"])
             self.user_mapping_ = np.require(umap, requirements=["ENSUREARRAY"]).reshape(-1)
             self.item_mapping_ = np.require(imap, requirements=["ENSUREARRAY"]).reshape(-1)
             self.nusers = self.user_mapping_.shape[0]
@@ -319,9 +319,21 @@ class HPF:
             if self.nusers < self.users_per_batch:
                 warnings.warn("Batch size passed is larger than number of users. Will set it to nusers/10.")
                 self.users_per_batch = int(np.ceil(self.nusers / 10))
-            frame.sort_values('UserId', inplace=True, kind="stable")
+            # the reference sorts the frame by user here (hpfrec/__init__.py:520) because its loops index the arrays
+            # through st_ix_u; the engine builds its own orderings on the device from unsorted triples, so the
+            # 48M-row host sort is skipped
             self._store_metadata(for_partial_fit=True)
         return None
+
+    def _factorize(self, column):
+        """pd.factorize (hpfrec/__init__.py:478-479).  Integer id columns are factorized on the device (two radix
+        sorts, hpf_factorize); anything else (strings, objects, floats) has no device representation and stays with
+        pandas.  Same result either way: codes in order of first appearance."""
+        values = column.to_numpy(copy=False) if hasattr(column, "to_numpy") else np.asarray(column)
+        if values.dtype.kind in "iu" and values.dtype.itemsize in (4, 8) and values.shape[0] > 0:
+            from .engine import factorize
+            return factorize(values, device=self._loops.device)
+        return pd.factorize(column)
 
     def _process_valset(self, val_set, valset=True):
         frame = _triplets_frame(val_set, "val_set")
@@ -363,18 +375,19 @@ class HPF:
     def _store_metadata(self, for_partial_fit=False):
         if self.verbose and for_partial_fit:
             print("Creating user indices for stochastic optimization...")
+        # the reference builds scipy's coo -> csr here (hpfrec/__init__.py:591-598) only for its indptr / indices; the
+        # same two arrays come from one device sort of the (user, item) pairs (hpf_csr_metadata)
+        from .engine import csr_metadata
         df = self.input_df
-        X = coo_array((df["Count"].to_numpy(copy=False),
-                       (df["UserId"].to_numpy(copy=False), df["ItemId"].to_numpy(copy=False))),
-                      shape=(self.nusers, self.nitems),
-                      dtype=self._loops.c_real_t).tocsr()
-        self._n_seen_by_user = X.indptr[1:] - X.indptr[:-1]
+        indptr, indices = csr_metadata(df["UserId"].to_numpy(copy=False), df["ItemId"].to_numpy(copy=False),
+                                       self.nusers, self.nitems, device=self._loops.device)
+        self._n_seen_by_user = indptr[1:] - indptr[:-1]
         if for_partial_fit:
-            self._st_ix_user = np.require(X.indptr, dtype=self._loops.obj_ind_type,
+            self._st_ix_user = np.require(indptr, dtype=self._loops.obj_ind_type,
                                           requirements=["ENSUREARRAY", "C_CONTIGUOUS"])
         else:
-            self._st_ix_user = X.indptr[:-1]
-        self.seen = X.indices
+            self._st_ix_user = indptr[:-1]
+        self.seen = indices
         return None
 
     def _cast_before_fit(self):
@@ -627,6 +640,36 @@ class HPF:
         if return_all:
             return (Theta, temp[0], temp[1], temp[2])
         return Theta
+
+    def predict_factors_batch(self, counts_df, maxiter=10, random_seed=1, stop_thr=1e-3, return_all=False):
+        """predict_factors for MANY new users at once (an extension; the reference folds in one user per call,
+        hpfrec/__init__.py:989-1058).  `counts_df`: (UserId, ItemId, Count) rows of users that need not be in the model;
+        items must be.  Every user receives exactly the factors a separate predict_factors call with the same seed
+        returns, but all users share one device engine: one user-major pass and one row update per iteration for the
+        whole batch.  Returns (user_ids, Theta) -- user_ids in order of first appearance, Theta (n_users, k) -- or with
+        return_all (user_ids, Theta, Gamma_shp, Gamma_rte)."""
+        _, random_seed, stop_thr, maxiter = self._check_input_predict_factors(1, random_seed, stop_thr, maxiter)
+        assert self.is_fitted and self.keep_all_objs
+        if isinstance(counts_df, np.ndarray):
+            assert counts_df.ndim == 2 and counts_df.shape[1] >= 3
+            counts_df = pd.DataFrame(counts_df[:, :3], columns=["UserId", "ItemId", "Count"])
+        assert isinstance(counts_df, pd.DataFrame) and counts_df.shape[0] > 0
+        for col in ("UserId", "ItemId", "Count"):
+            assert col in counts_df.columns
+        codes, user_ids = pd.factorize(counts_df["UserId"].to_numpy(copy=False))
+        items = self._process_data_single(counts_df[["ItemId", "Count"]])
+        lp = self._loops
+        out = lp.calc_user_factors_batch(
+            self.a, self.a_prime, self.b_prime, self.c, self.c_prime, self.d_prime,
+            items["Count"].to_numpy(copy=False), codes.astype(np.int64), items["ItemId"].to_numpy(copy=False),
+            self.Beta, self.Lambda_shp, self.Lambda_rte, int(user_ids.shape[0]), int(self.k), int(maxiter),
+            int(random_seed), lp.cast_real_t(stop_thr), return_all=bool(return_all))
+        Theta = out[0] if return_all else out
+        if np.isnan(Theta).sum() > 0:
+            raise ValueError("NaNs encountered in the result. Failed to produce latent factors.")
+        if return_all:
+            return user_ids, Theta, out[1], out[2]
+        return user_ids, Theta
 
     def add_user(self, user_id, counts_df, update_existing=False, maxiter=10, ncores=1,
                  random_seed=1, stop_thr=1e-3, update_all_params=None):

@@ -40,6 +40,7 @@ SIGNATURES = {
     "hpf_adopt_item_buffers": ([_P, _c.POINTER(_P)], _c.c_int),
     "hpf_peer_attach_ptrs": ([_P, _I32, _I32, _c.POINTER(_P), _c.POINTER(_P)], _c.c_int),
     "hpf_update_items_peer": ([_P, _I32], _c.c_int),
+    "hpf_reduce_items_peer": ([_P, _P], _c.c_int),
     "hpf_peer_finish": ([_P], _c.c_int),
     "hpf_beta_colsum": ([_P, _c.POINTER(_P), _c.POINTER(_I64)], _c.c_int),
     "hpf_step_batch": ([_P, _P, _P, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _D, _D, _I32], _c.c_int),
@@ -56,6 +57,8 @@ SIGNATURES = {
     "hpf_update_shapes": ([_I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I32, _D, _D],
                           _c.c_int),
     "hpf_digamma": ([_I32, _I32, _P, _P, _I64], _c.c_int),
+    "hpf_factorize": ([_I32, _P, _I64, _I32, _P, _I32, _P, _c.POINTER(_I64)], _c.c_int),
+    "hpf_csr_metadata": ([_I32, _P, _P, _I64, _I32, _I64, _I64, _P, _P, _I32, _c.POINTER(_I64)], _c.c_int),
     "hpf_trim_cache": ([], _c.c_int),
     "hpf_launch_count": ([_P, _c.POINTER(_I64)], _c.c_int),
     "hpf_phase_ms": ([_P, _c.POINTER(_D), _c.POINTER(_I64)], _c.c_int),

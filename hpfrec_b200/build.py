@@ -17,7 +17,7 @@ LIB = os.path.join(OUT_DIR, "libhpf_b200.so")
 PROBE_SRC = os.path.join(HERE, "..", "tools", "gather_probe.cu")
 PROBE_BIN = os.path.join(HERE, "..", "tools", "bin", "gather_probe")
 SOURCES = ["hpf_engine.cu"]
-DEPS = ["hpf_engine.cu", "hpf_kernels.cuh", "hpf_batch.cuh", "hpf_device.cuh", "hpf_batch_host.inl", "hpf_sweep_dispatch.inl", "hpf_sweep.cuh", "hpf_scorer.inl",
+DEPS = ["hpf_engine.cu", "hpf_kernels.cuh", "hpf_batch.cuh", "hpf_device.cuh", "hpf_batch_host.inl", "hpf_sweep_dispatch.inl", "hpf_sweep.cuh", "hpf_scorer.inl", "hpf_ingest.inl",
         os.path.join("..", "..", "include", "hpf_b200.h")]
 
 NVCC_FLAGS = [

@@ -236,10 +236,14 @@ __device__ __forceinline__ double rdiv_rcp(double a, double b) { return a / b; }
 // then the asymptotic series log(x) - 1/(2x) - sum_n B_2n / (2n x^2n).  Same scheme here (7 Bernoulli
 // terms in double).  Validated against scipy on a dense grid in
 // tests/test_gpu_parity.py::test_digamma_vs_scipy.
-__device__ __forceinline__ double digamma(double x) {
-    double acc = 0.0;
+// The recurrence's sum of reciprocals is carried as ONE fraction (num/den += 1/x  <=>  num = num*x + den, den *= x):
+// one fp64 division per call instead of up to ten (shapes near the prior need all ten steps; the fp64 row update
+// was spending most of its instructions there).  3e-15 vs scipy on the test grid (the per-step divisions: 1.5e-15).
+__device__ __forceinline__ void digamma_parts(double x, double& z, double& tail) {
+    double num = 0.0, den = 1.0;
     while (x < 10.0) {
-        acc -= 1.0 / x;
+        num = fma(num, x, den);
+        den *= x;
         x += 1.0;
     }
     const double r = 1.0 / x;
@@ -251,7 +255,13 @@ __device__ __forceinline__ double digamma(double x) {
     p = fma(p, r2, 3.96825396825396825397e-3);          //  1/252
     p = fma(p, r2, -8.33333333333333333333e-3);         // -1/120
     p = fma(p, r2, 8.33333333333333333333e-2);          //  1/12   (x^-2)
-    return acc + (log(x) - 0.5 * r - r2 * p);
+    z = x;
+    tail = (-0.5 * r - r2 * p) - num / den;             // psi(x) = log(z) + tail
+}
+__device__ __forceinline__ double digamma(double x) {
+    double z, tail;
+    digamma_parts(x, z, tail);
+    return log(z) + tail;
 }
 // float: psi(z) = log z - 1/(2z) - t*P3(t), t = 1/z^2, valid to 1 ulp for z >= 2 (P3 = degree-3
 // least-squares fit of the asymptotic tail on t in (0, 1/4], fitted against scipy in double);
@@ -283,7 +293,12 @@ __device__ __forceinline__ float elog(float shape, float rate) {
     digamma_parts(shape, z, tail);
     return logf(__fdividef(z, rate)) + tail;
 }
-__device__ __forceinline__ double elog(double shape, double rate) { return digamma(shape) - log(rate); }
+// double: likewise one logarithm, log(z / rate) (z >= 10 after the recurrence; one more rounding of 1 ulp)
+__device__ __forceinline__ double elog(double shape, double rate) {
+    double z, tail;
+    digamma_parts(shape, z, tail);
+    return log(z / rate) + tail;
+}
 
 // expectation shape / rate: IEEE in double; 2-ulp MUFU quotient in float
 __device__ __forceinline__ float rratio(float a, float b) { return __fdividef(a, b); }

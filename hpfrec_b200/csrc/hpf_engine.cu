@@ -299,6 +299,7 @@ struct hpf_engine {
     bool peer_attached = false;
     bool peer_multicast = false;  // peers.mc_* are valid: the exchange kernel uses multimem.ld_reduce / multimem.st
     bool ipc_exported = false;    // the item-side buffers were handed out with hpf_peer_export
+    bool items_pre_reduced = false;  // hpf_reduce_items_peer has left the all-rank item sums of the owned slice in accI
     bool items_adopted = false;   // the five item-side buffers belong to the caller (symmetric memory): never freed here
     std::vector<void*> ipc_opened;
     // minibatch membership stamps (allocated at the first hpf_step_batch)
@@ -1240,25 +1241,55 @@ int hpf_update_items_peer(hpf_engine* h, int32_t materialize) {
             const int grid = row_grid(r1 - r0, C::lpg);
             const size_t smem = sizeof(double) * h->ld;
             const real prior = (real)h->c, shp_rate = (real)h->t_shp, add_rate = (real)h->add_t;
+            const int pre = h->items_pre_reduced ? 1 : 0;
             if (h->peer_multicast) {
                 if (materialize)
                     hpf::update_items_peer_kernel<real, C::lpg, C::vpl, true, true><<<grid, 256, smem, h->stream>>>(
-                        r0, r1, h->ld, h->k, h->peers, h->Tsum, h->Bsum, prior, shp_rate, add_rate);
+                        r0, r1, h->ld, h->k, h->peers, h->Tsum, h->Bsum, prior, shp_rate, add_rate, pre);
                 else
                     hpf::update_items_peer_kernel<real, C::lpg, C::vpl, false, true><<<grid, 256, smem, h->stream>>>(
-                        r0, r1, h->ld, h->k, h->peers, h->Tsum, h->Bsum, prior, shp_rate, add_rate);
+                        r0, r1, h->ld, h->k, h->peers, h->Tsum, h->Bsum, prior, shp_rate, add_rate, pre);
             } else if (materialize)
                 hpf::update_items_peer_kernel<real, C::lpg, C::vpl, true, false><<<grid, 256, smem, h->stream>>>(
-                    r0, r1, h->ld, h->k, h->peers, h->Tsum, h->Bsum, prior, shp_rate, add_rate);
+                    r0, r1, h->ld, h->k, h->peers, h->Tsum, h->Bsum, prior, shp_rate, add_rate, pre);
             else
                 hpf::update_items_peer_kernel<real, C::lpg, C::vpl, false, false><<<grid, 256, smem, h->stream>>>(
-                    r0, r1, h->ld, h->k, h->peers, h->Tsum, h->Bsum, prior, shp_rate, add_rate);
+                    r0, r1, h->ld, h->k, h->peers, h->Tsum, h->Bsum, prior, shp_rate, add_rate, pre);
             h->launches++;
             CKK();
             return HPF_OK;
         }));
     }
+    h->items_pre_reduced = false;
     h->mat_valid = materialize != 0;
+    return HPF_OK;
+}
+
+int hpf_reduce_items_peer(hpf_engine* h, void* stream) {
+    if (!h) return fail(HPF_EINVAL, "engine is NULL");
+    if (!h->peer_attached) return fail(HPF_ESTATE, "hpf_peer_attach has not been called");
+    if (!h->x_valid) return fail(HPF_ESTATE, "hpf_reduce_items_peer must follow the item-major pass");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    const int r0 = (int)(h->nI * (int64_t)h->peers.rank / h->peers.world);
+    const int r1 = (int)(h->nI * (int64_t)(h->peers.rank + 1) / h->peers.world);
+    if (r1 > r0) {
+        TRY(dispatch(h->rb, h->ld, [&](auto cfg) {
+            using C = decltype(cfg);
+            using real = typename C::real;
+            // NVLink-bound, and it shares the SMs with the user-major pass: two CTAs per SM at most
+            int grid = row_grid(r1 - r0, C::lpg);
+            if (grid > 148 * 2) grid = 148 * 2;
+            if (h->peer_multicast)
+                hpf::reduce_items_peer_kernel<real, C::lpg, C::vpl, true><<<grid, 256, 0, st>>>(r0, r1, h->ld, h->k, h->peers);
+            else
+                hpf::reduce_items_peer_kernel<real, C::lpg, C::vpl, false><<<grid, 256, 0, st>>>(r0, r1, h->ld, h->k, h->peers);
+            h->launches++;
+            CKK();
+            return HPF_OK;
+        }));
+    }
+    h->items_pre_reduced = true;
     return HPF_OK;
 }
 
@@ -1551,3 +1582,4 @@ int hpf_digamma(int32_t real_bytes, int32_t device, const void* x, void* out, in
 
 #include "hpf_batch_host.inl"
 #include "hpf_scorer.inl"
+#include "hpf_ingest.inl"

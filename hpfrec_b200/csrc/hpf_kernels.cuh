@@ -177,7 +177,7 @@ __device__ __forceinline__ void mc_st_scalar(double* p, double v) {
 template <typename real, int LPG, int VPL, bool MAT, bool MC>
 __global__ void __launch_bounds__(256)
 update_items_peer_kernel(int r0, int r1, int ld, int k, PeerTable pt, const double* __restrict__ colsum_other,
-                         double* __restrict__ colsum_out, real prior, real shp_rate, real add_rate) {
+                         double* __restrict__ colsum_out, real prior, real shp_rate, real add_rate, int pre_reduced) {
     constexpr int EPV = Pack<real>::N;
     extern __shared__ double s_col[];
     for (int j = threadIdx.x; j < ld; j += blockDim.x) s_col[j] = 0.0;
@@ -212,12 +212,16 @@ update_items_peer_kernel(int r0, int r1, int ld, int k, PeerTable pt, const doub
         // ~2 us latency, so memory-level parallelism per thread is what fills the links
 #pragma unroll
         for (int v = 0; v < VPL; ++v) asum[v] = pack_zero<real>();
-        if (MC) {
+        if (pre_reduced) {  // reduce_items_peer_kernel already left the all-rank sums in this rank's own buffer
+#pragma unroll
+            for (int v = 0; v < VPL; ++v)
+                if (act[v]) asum[v] = ld_pack((const real*)pt.acc[pt.rank] + (size_t)r * ld + off[v]);
+        } else if (MC) {
 #pragma unroll
             for (int v = 0; v < VPL; ++v)
                 if (act[v]) asum[v] = mc_ld_reduce((const real*)pt.mc_acc + (size_t)r * ld + off[v]);
         }
-        for (int p0 = 0; !MC && p0 < pt.world; p0 += 8) {
+        for (int p0 = 0; !MC && !pre_reduced && p0 < pt.world; p0 += 8) {
             Pack<real> pv[VPL][8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -294,6 +298,61 @@ update_items_peer_kernel(int r0, int r1, int ld, int k, PeerTable pt, const doub
     }
     __syncthreads();
     for (int j = threadIdx.x; j < k; j += blockDim.x) atomicAdd(colsum_out + j, s_col[j]);
+}
+
+// =============================================================================================
+// The reduce-scatter half of the exchange on its own, so that it can run on a second stream UNDER the user-major
+// pass and the user update (it only needs every rank's item-major pass to be finished): rank `rank` sums its slice
+// of item rows over all ranks' partial sums -- one multimem.ld_reduce per pack (MC) or P2P loads in fixed rank order
+// -- and leaves the totals in its OWN buffer, in place (no other rank ever reads those rows of this buffer).
+// update_items_peer_kernel then runs with pre_reduced = 1.
+// =============================================================================================
+template <typename real, int LPG, int VPL, bool MC>
+__global__ void __launch_bounds__(256)
+reduce_items_peer_kernel(int r0, int r1, int ld, int k, PeerTable pt) {
+    constexpr int EPV = Pack<real>::N;
+    const int gl = (threadIdx.x & 31) % LPG;
+    const int groups_per_block = blockDim.x / LPG;
+    const int g0 = blockIdx.x * groups_per_block + threadIdx.x / LPG;
+    const int gstride = gridDim.x * groups_per_block;
+    real* mine = (real*)pt.acc[pt.rank];
+    int off[VPL];
+    bool act[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        off[v] = (gl + LPG * v) * EPV;
+        act[v] = off[v] < k;
+    }
+    for (int r = r0 + g0; r < r1; r += gstride) {
+        Pack<real> asum[VPL];
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) asum[v] = pack_zero<real>();
+        if (MC) {
+#pragma unroll
+            for (int v = 0; v < VPL; ++v)
+                if (act[v]) asum[v] = mc_ld_reduce((const real*)pt.mc_acc + (size_t)r * ld + off[v]);
+        }
+        for (int p0 = 0; !MC && p0 < pt.world; p0 += 8) {
+            Pack<real> pv[VPL][8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const bool have = p0 + q < pt.world;
+                const real* base = (const real*)pt.acc[have ? p0 + q : pt.rank];
+#pragma unroll
+                for (int v = 0; v < VPL; ++v)
+                    pv[v][q] = (have && act[v]) ? ld_pack(base + (size_t)r * ld + off[v]) : pack_zero<real>();
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)  // the same fixed rank order as the fused kernel: identical bits
+#pragma unroll
+                for (int v = 0; v < VPL; ++v)
+#pragma unroll
+                    for (int e = 0; e < EPV; ++e) asum[v].v[e] += pv[v][q].v[e];
+        }
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+            if (act[v]) st_pack(mine + (size_t)r * ld + off[v], asum[v]);
+    }
 }
 
 // =============================================================================================

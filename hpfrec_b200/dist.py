@@ -7,6 +7,8 @@ The prior `c` is added once, after the reduction (inside hpf_update_items), neve
 then recomputes the identical item update from identical reduced data, so replicas stay bit-identical
 without a broadcast.
 """
+import os
+
 import numpy as np
 
 
@@ -167,12 +169,27 @@ def attach_symmetric(engine, group=None, multicast=True):
     return hdl, t, bool(mc_base)
 
 
-def run_sharded_iterations_peer(engine, niter, group=None, materialize_last=True):
-    """User-sharded iterations with the item-side exchange fused into ONE kernel over NVLink peer
-    memory (hpf_update_items_peer): each rank reduces its slice of item rows straight out of the other
-    ranks' partial-sum buffers, updates it, and stores the result into every replica.  The only NCCL
-    traffic left is two k-double all-reduces per iteration (Theta and Beta column sums), which double
-    as the two cross-GPU barriers the kernel needs."""
+_side_streams = {}
+
+
+def _side_stream(dev):
+    """One high-priority side stream per device for the overlapped reduce-scatter."""
+    import torch
+    if dev not in _side_streams:
+        _side_streams[dev] = (torch.cuda.Stream(device=dev, priority=-1), torch.zeros(1, dtype=torch.float32, device=dev))
+    return _side_streams[dev]
+
+
+def run_sharded_iterations_peer(engine, niter, group=None, materialize_last=True, overlap=True):
+    """User-sharded iterations with the item-side exchange over NVLink peer / NVSwitch multicast memory: each rank
+    reduces its slice of item rows straight out of all ranks' partial-sum buffers, updates it, and stores the result
+    into every replica.  The only NCCL traffic is k-double all-reduces (Theta and Beta column sums), which double as
+    the cross-GPU barriers the kernels need.
+
+    overlap=True splits the exchange: the reduce-scatter half (hpf_reduce_items_peer) starts right after the
+    item-major pass on a second stream -- behind one extra barrier that makes every rank's partial sums final -- and
+    runs UNDER the user-major pass and the user update; the update + broadcast half follows on the main stream.
+    overlap=False is the single fused kernel after both passes."""
     import torch
     import torch.distributed as dist
     dev = torch.cuda.current_device()
@@ -180,12 +197,22 @@ def run_sharded_iterations_peer(engine, niter, group=None, materialize_last=True
     p_beta, n_beta = engine.beta_colsum()
     t_theta = wrap_device_buffer(p_theta, n_theta, torch.float64, dev)
     t_beta = wrap_device_buffer(p_beta, n_beta, torch.float64, dev)
+    main = torch.cuda.current_stream()
+    if overlap:
+        side, t_bar = _side_stream(dev)
     for it in range(int(niter)):
         last = materialize_last and it == niter - 1
         engine.sweep_side(0)
+        if overlap:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                _all_reduce_device(t_bar, group)            # every rank's item-major pass is done
+                engine.reduce_items_peer(side.cuda_stream)
         engine.sweep_side(1)
         engine.update_users(last)
         _all_reduce_device(t_theta, group)
+        if overlap:
+            main.wait_stream(side)
         engine.update_items_peer(last)
         _all_reduce_device(t_beta, group)
         engine.peer_finish()
@@ -206,7 +233,7 @@ class ShardedLoop:
           "auto"    "nvls" with NCCL, else "peer"
     Construct it BEFORE hpf_load_state (the fused modes map the engine's item-side buffers into every rank)."""
 
-    def __init__(self, engine, mode="auto", group=None, graph=False):
+    def __init__(self, engine, mode="auto", group=None, graph=False, overlap=None):
         import torch
         import torch.distributed as dist
         self.engine, self.group = engine, group
@@ -228,6 +255,8 @@ class ShardedLoop:
                 warnings.warn("symmetric memory unavailable (%r): using the CUDA-IPC peer exchange" % (exc,))
                 mode = "peer"
         self.mode = mode
+        #: reduce-scatter half of the fused exchange on a second stream, under the user-major pass (HPF_EXCHANGE_OVERLAP=0: off)
+        self.overlap = (os.environ.get("HPF_EXCHANGE_OVERLAP", "1") != "0") if overlap is None else bool(overlap)
         self.use_graph = bool(graph) and self.world > 1
         self.stream = torch.cuda.Stream() if self.use_graph else torch.cuda.current_stream()
         self.graph = None
@@ -244,7 +273,7 @@ class ShardedLoop:
         if self.mode == "single":
             self.engine.step_full(n)
         elif self.mode in ("peer", "nvls", "symm"):
-            run_sharded_iterations_peer(self.engine, n, self.group, materialize_last=materialize_last)
+            run_sharded_iterations_peer(self.engine, n, self.group, materialize_last=materialize_last, overlap=self.overlap)
         elif self.mode == "overlap":
             run_sharded_iterations_overlapped(self.engine, n, group=self.group)
         else:

@@ -217,6 +217,10 @@ class Engine:
     def update_items_peer(self, materialize=True):
         _lib.check(self._lib.hpf_update_items_peer(self._h, int(bool(materialize))))
 
+    def reduce_items_peer(self, stream=None):
+        """The reduce-scatter half of the exchange alone, on `stream` (raw cudaStream_t handle; None = the engine's)."""
+        _lib.check(self._lib.hpf_reduce_items_peer(self._h, ctypes.c_void_p(int(stream) if stream else None)))
+
     def peer_finish(self):
         _lib.check(self._lib.hpf_peer_finish(self._h))
 
@@ -288,6 +292,38 @@ def digamma(x, device=0):
     out = np.empty_like(x)
     _lib.check(lib.hpf_digamma(x.dtype.itemsize, int(device), _ptr(x), _ptr(out), int(x.size)))
     return out
+
+
+def factorize(values, device=0):
+    """pd.factorize of an integer id column on the device (hpf_factorize): returns (codes int64, uniques in the
+    column's own dtype), codes numbered in order of first appearance exactly like pandas."""
+    lib = _lib.load()
+    v = np.ascontiguousarray(values).reshape(-1)
+    if v.dtype.kind not in "iu" or v.dtype.itemsize not in (4, 8):
+        raise ValueError("device factorize needs a 32- or 64-bit integer column, got %s" % v.dtype)
+    n = int(v.shape[0])
+    codes = np.empty(n, dtype=np.int64)
+    uniques = np.empty(n, dtype=v.dtype)
+    n_unique = ctypes.c_int64(0)
+    _lib.check(lib.hpf_factorize(int(device), _ptr(v), n, v.dtype.itemsize, _ptr(codes), 8, _ptr(uniques),
+                                 ctypes.byref(n_unique)))
+    return codes, uniques[:n_unique.value].copy()
+
+
+def csr_metadata(ix_u, ix_i, nU, nI, device=0):
+    """(indptr, indices) of coo_array((.., (ix_u, ix_i)), shape=(nU, nI)).tocsr() built on the device
+    (hpf_csr_metadata): duplicate pairs merged, item ids ascending within a user; int32 like scipy's at these sizes."""
+    lib = _lib.load()
+    u, i = as_index(ix_u), as_index(ix_i)
+    if u.dtype.itemsize != i.dtype.itemsize:
+        u, i = u.astype(np.int64), i.astype(np.int64)
+    n = int(u.shape[0])
+    indptr = np.empty(int(nU) + 1, dtype=np.int64)
+    indices = np.empty(max(n, 1), dtype=np.int32)
+    n_out = ctypes.c_int64(0)
+    _lib.check(lib.hpf_csr_metadata(int(device), _ptr(u), _ptr(i), n, u.dtype.itemsize, int(nU), int(nI),
+                                    _ptr(indptr), _ptr(indices), 4, ctypes.byref(n_out)))
+    return indptr.astype(np.int32), indices[:n_out.value].copy()
 
 
 class Scorer:

@@ -326,10 +326,14 @@ class CudaLoops:
             eng.load_coo(np.zeros(int(nY), dtype=np.int64), ix_i, Y)                  # pxi:501 (all-zero ix_u)
             th = np.empty((1, k), dtype=dt)
             G_read, R_read = Gamma_shp.copy(), Gamma_rte.copy()   # state the last update_phi read (for phi)
+            user_pass_only = eng.describe().get("robust") != "1"   # the item side is frozen: its sums are never used
             for _ in range(int(maxiter)):
                 if return_all:
                     eng.export_state(Gamma_shp=G_read, Gamma_rte=R_read)
-                eng.sweep()
+                if user_pass_only:
+                    eng.sweep_side(1)
+                else:
+                    eng.sweep()
                 eng.update_users()                                                     # pxi:507-510
                 eng.export_state(Theta=th)
                 Theta[:] = th[0]
@@ -349,6 +353,71 @@ class CudaLoops:
         update_shapes(G_tmp, R_read, L_tmp, np.ascontiguousarray(Lambda_rte, dt), Y,
                       np.zeros(int(nY), dtype=np.int64), ix_i, a, c, phi=phi, device=self.device)
         return Gamma_shp.reshape(-1), Gamma_rte.reshape(-1), phi / Y.reshape((-1, 1))
+
+    def calc_user_factors_batch(self, a, a_prime, b_prime, c, c_prime, d_prime, Y, ix_u, ix_i, Beta, Lambda_shp, Lambda_rte,
+                                n_users, k, maxiter, random_seed, stop_thr, return_all=False):
+        """calc_user_factors (pxi:476-520) for MANY new users in one engine: `ix_u` numbers the new users 0..n_users-1,
+        the item side is frozen.  Every user gets exactly what a separate calc_user_factors call with the same
+        `random_seed` gives her (the reference seeds its generator per call, so all users start from the same draw; a
+        user's iterations never read another user's rows), including her own early stop: the device keeps iterating
+        all rows, the host freezes each user's result at the first iteration where ||Theta_t - Theta_{t-1}|| < stop_thr.
+        Per iteration: ONE user-major pass + ONE row update for all users, one (n_users x k) read-back.
+        Returns Theta (n_users, k), or (Theta, Gamma_shp, Gamma_rte, n_iter) with return_all."""
+        dt = self.dtype
+        k, B = int(k), int(n_users)
+        nI = Beta.shape[0]
+        k_shp = dt.type(a_prime + k * a)
+        rng = np.random.default_rng(seed=random_seed if random_seed > 0 else None)
+        theta0 = rng.gamma(a, 1 / b_prime, size=k).astype(dt)                              # pxi:491
+        k_rte0 = dt.type(b_prime + theta0.sum())                                            # pxi:492
+        rte0 = rng.gamma(a_prime, b_prime / a_prime, size=1).astype(dt) + Beta.sum(axis=0)  # pxi:493
+        shp0 = rte0 * theta0 * rng.uniform(low=.85, high=1.15, size=k).astype(dt)          # pxi:495
+        np.nan_to_num(shp0, copy=False)
+        np.nan_to_num(rte0, copy=False)
+        Y = np.ascontiguousarray(Y, dtype=dt)
+        ix_u, ix_i = as_index(ix_u).astype(np.int64), as_index(ix_i).astype(np.int64)
+        if ix_u.shape[0] and (ix_u.min() < 0 or ix_u.max() >= B):
+            raise ValueError("user numbers must lie in [0, n_users)")
+        Theta = np.tile(theta0.astype(dt), (B, 1))
+        out_shp = np.tile(shp0.astype(dt), (B, 1))
+        out_rte = np.tile(rte0.astype(dt), (B, 1))
+        n_iter = np.zeros(B, dtype=np.int64)
+        active = np.ones(B, dtype=bool)
+        prev = Theta.copy()
+        eng = self._engine(B, nI, k)
+        try:
+            eng.set_hyper(a, a_prime, b_prime, c, c_prime, d_prime)
+            eng.load_state(np.ascontiguousarray(out_shp), np.ascontiguousarray(out_rte), np.ascontiguousarray(Lambda_shp, dt),
+                           np.ascontiguousarray(Lambda_rte, dt), np.full((B, 1), k_rte0, dtype=dt), np.ones((nI, 1), dtype=dt))
+            eng.load_coo(ix_u, ix_i, Y)
+            user_pass_only = eng.describe().get("robust") != "1"
+            th = np.empty((B, k), dtype=dt)
+            gs = np.empty((B, k), dtype=dt) if return_all else None
+            gr = np.empty((B, k), dtype=dt) if return_all else None
+            for _ in range(int(maxiter)):
+                if user_pass_only:
+                    eng.sweep_side(1)
+                else:
+                    eng.sweep()
+                eng.update_users()                                                          # pxi:507-510, all users at once
+                if return_all:
+                    eng.export_state(Gamma_shp=gs, Gamma_rte=gr, Theta=th)
+                else:
+                    eng.export_state(Theta=th)
+                Theta[active] = th[active]
+                n_iter[active] += 1
+                if return_all:
+                    out_shp[active], out_rte[active] = gs[active], gr[active]
+                done = active & (np.linalg.norm(th - prev, axis=1) < stop_thr)              # pxi:513, per user
+                active &= ~done
+                if not active.any():
+                    break
+                prev[active] = th[active]
+        finally:
+            eng.close()
+        if return_all:
+            return Theta, out_shp, out_rte, n_iter
+        return Theta
 
     # ---- calc_llk (pxi:525-534) / predict_arr (pxi:538-543) --------------------------------------------
     def _factors_engine(self, Theta, Beta):

@@ -142,6 +142,12 @@ int hpf_item_buffer_bytes(hpf_engine* h, int64_t out[HPF_PEER_BUFFERS]);
 int hpf_adopt_item_buffers(hpf_engine* h, void* const bufs[HPF_PEER_BUFFERS]);
 int hpf_peer_attach_ptrs(hpf_engine* h, int32_t rank, int32_t world, void* const* peer_ptrs, void* const* mc_ptrs);
 int hpf_update_items_peer(hpf_engine* h, int32_t materialize);
+/* Optional split of the exchange: the reduce-scatter half alone, launched on `stream` (a cudaStream_t; NULL = the
+ * engine's stream) so that it can overlap the user-major pass and hpf_update_users.  It needs every rank's item-major
+ * pass (hpf_sweep_side(h, 0)) to be complete -- the caller puts a cross-rank barrier before it -- and leaves the
+ * all-rank sums of this rank's slice in its own item_sums buffer; the next hpf_update_items_peer (which the caller
+ * orders after it) then skips its own reduction. */
+int hpf_reduce_items_peer(hpf_engine* h, void* stream);
 int hpf_peer_finish(hpf_engine* h);
 int hpf_beta_colsum(hpf_engine* h, void** ptr, int64_t* count);
 
@@ -238,6 +244,23 @@ int hpf_phase_ms(hpf_engine* h, double out[4], int64_t* iterations);
 int hpf_describe(hpf_engine* h, char* buf, int64_t n);
 /* Leading dimension (padded k) of the engine's device matrices. */
 int hpf_ld(hpf_engine* h, int32_t* out);
+
+/* ---- ingest on the device (the host-side pandas / scipy steps of HPF._process_data and HPF._store_metadata) -------- */
+
+/* pd.factorize of an INTEGER id column (hpfrec/__init__.py:478-479): codes_out[j] = dense code of values[j], numbered
+ * in order of first appearance; uniques_out[c] = the id with code c.  values: n ids of value_bytes (4 or 8) [h|d];
+ * codes_out: n integers of code_bytes (4 or 8) [h|d]; uniques_out: room for n ids of value_bytes [h|d];
+ * *n_unique (host) receives the number of distinct ids.  One stable radix sort of (id, position), one of the runs'
+ * first positions, three one-pass kernels.  n < 2^31. */
+int hpf_factorize(int32_t device, const void* values, int64_t n, int32_t value_bytes, void* codes_out, int32_t code_bytes,
+                  void* uniques_out, int64_t* n_unique);
+
+/* The CSR arrays HPF._store_metadata keeps (hpfrec/__init__.py:587-606: coo_array(...).tocsr(), i.e. duplicates of a
+ * (user, item) pair merged and item ids ascending within a user): indptr_out = nU + 1 int64 [h|d], indices_out = room
+ * for n item ids of out_index_bytes (4 or 8) [h|d], *n_out (host) = number of distinct pairs.  Out-of-range indices are
+ * rejected with HPF_EINVAL. */
+int hpf_csr_metadata(int32_t device, const void* ix_u, const void* ix_i, int64_t n, int32_t index_bytes, int64_t nU, int64_t nI,
+                     int64_t* indptr_out, void* indices_out, int32_t out_index_bytes, int64_t* n_out);
 
 #ifdef __cplusplus
 }

@@ -108,13 +108,15 @@ def test_constructor_validation_matches_reference_rules():
 
 
 def test_process_data_reindex_and_filtering():
+    """Host logic of HPF._process_data that needs no device: string ids stay with pandas, zero counts are dropped,
+    dtypes follow use_float, a COO input switches reindexing off."""
     from hpfrec_b200 import HPF
-    df = pd.DataFrame({"UserId": ["b", "a", "b", "c"], "ItemId": [10, 10, 30, 20], "Count": [1, 2, 0, 3]})
+    df = pd.DataFrame({"UserId": ["b", "a", "b", "c"], "ItemId": ["x", "x", "z", "y"], "Count": [1, 2, 0, 3]})
     m = HPF(k=3, verbose=False)
     with pytest.warns(UserWarning):
         m._process_data(df)
-    assert m.nusers == 3 and m.nitems == 2                    # the zero-count row (b,30) is dropped
-    assert m.user_mapping_.tolist() == ["b", "a", "c"]
+    assert m.nusers == 3 and m.nitems == 2                    # the zero-count row (b,z) is dropped
+    assert m.user_mapping_.tolist() == ["b", "a", "c"] and m.item_mapping_.tolist() == ["x", "y"]
     assert m.input_df["UserId"].tolist() == [0, 1, 2]
     assert m.input_df["Count"].dtype == np.float32
 
@@ -125,10 +127,17 @@ def test_process_data_reindex_and_filtering():
     assert m2.reindex is False and (m2.nusers, m2.nitems) == (6, 5)
     assert m2.input_df["Count"].dtype == np.float64
 
-    m3 = HPF(k=3, verbose=False, users_per_batch=2, reindex=False)
-    m3._process_data(np.array([[3, 0, 1.], [0, 1, 2.], [3, 1, 1.], [1, 0, 5.]]))
-    assert m3.input_df["UserId"].tolist() == [0, 1, 3, 3]
-    assert m3._st_ix_user.tolist() == [0, 1, 2, 2, 4]
+
+def test_integer_id_ingest_needs_the_device():
+    """Integer id columns are factorized by the CUDA library; without a GPU that fails loudly (no pandas fallback)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from hpfrec_b200 import HPF
+    from hpfrec_b200._lib import HPFError
+    df = pd.DataFrame({"UserId": [3, 1, 3], "ItemId": [10, 10, 30], "Count": [1, 2, 3]})
+    with pytest.raises(HPFError):
+        HPF(k=3, verbose=False)._process_data(df)
 
 
 def test_oracle_llk_shortcut_is_consistent():

@@ -21,10 +21,13 @@ fi
 if has bench; then
 for MODE in ${BENCH_MODES:-nvls peer}; do
 for GRAPH in ${BENCH_GRAPH:-1 0}; do
-log "bench N=$N exchange=$MODE graph=$GRAPH"
-HPF_MULTI=$MODE HPF_GRAPH=$GRAPH timeout 300 $TR --master-port 29542 bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline ${BENCH_ARGS:-} \
-    > $OUT/bench_N${N}_${MODE}_g$GRAPH.json 2> $OUT/bench_N${N}_${MODE}_g$GRAPH.err
-log "  rc=$? $(cut -c1-230 $OUT/bench_N${N}_${MODE}_g$GRAPH.json)"
+for OVL in ${BENCH_OVERLAP:-1 0}; do
+log "bench N=$N exchange=$MODE graph=$GRAPH overlap=$OVL"
+TAG=N${N}_${MODE}_g${GRAPH}_o$OVL
+HPF_MULTI=$MODE HPF_GRAPH=$GRAPH HPF_EXCHANGE_OVERLAP=$OVL timeout 300 $TR --master-port 29542 bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline ${BENCH_ARGS:-} \
+    > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
+log "  rc=$? $(cut -c1-230 $OUT/bench_$TAG.json)"
+done
 done
 done
 fi
