@@ -377,7 +377,7 @@ def run_ours(a):
     ld = eng.ld
     engine_config = eng.describe()
     if runner is not None:
-        engine_config["exchange"] = runner.mode
+        engine_config["exchange"] = runner.describe()
 
     svi_state = None
     if svi:

@@ -169,6 +169,39 @@ def attach_symmetric(engine, group=None, multicast=True):
     return hdl, t, bool(mc_base)
 
 
+class _PhaseTimer:
+    """HPF_PHASES=1: CUDA events between the phases of the eager sharded loop (main stream), summed over iterations
+    and printed by every rank as one `PHASES {...}` JSON line."""
+
+    totals = {}
+    iterations = 0
+
+    def __init__(self):
+        self.events = []
+
+    def mark(self, name):
+        import torch
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self.events.append((name, ev))
+
+    def report(self):
+        import json
+        import torch
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        cls = _PhaseTimer
+        for (n0, e0), (n1, e1) in zip(self.events[:-1], self.events[1:]):
+            if n1 == "start":
+                continue
+            cls.totals[n1] = cls.totals.get(n1, 0.0) + e0.elapsed_time(e1)
+        cls.iterations += sum(1 for n, _ in self.events if n == "start")
+        per = {k: round(v / max(cls.iterations, 1), 4) for k, v in cls.totals.items()}
+        per["sum"] = round(sum(per.values()), 4)
+        print("PHASES " + json.dumps({"rank": dist.get_rank() if dist.is_initialized() else 0, "iterations": cls.iterations,
+                                      "ms_per_iteration": per}), flush=True)
+
+
 _side_streams = {}
 
 
@@ -180,11 +213,58 @@ def _side_stream(dev):
     return _side_streams[dev]
 
 
-def run_sharded_iterations_peer(engine, niter, group=None, materialize_last=True, overlap=True):
+class SymmSync:
+    """Cross-GPU synchronisation of the sharded loop over symmetric memory instead of NCCL: device-side barriers on
+    the allocation's signal pads (one tiny kernel, a few microseconds, against ~20 us for a k-double NCCL all-reduce)
+    and the two k-double column-sum exchanges as "publish my partial, barrier, add everybody's partials in rank
+    order" (every rank adds the same numbers in the same order: bit-identical sums on all ranks)."""
+
+    TIMEOUT_MS = 20000   # a barrier that is not met traps instead of hanging the GPU
+
+    def __init__(self, n, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.n = int(n)
+        self.buf = symm_mem.empty(2 * self.n, dtype=torch.float64, device=dev)
+        self.hdl = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.buf.zero_()
+        self.views = [self.hdl.get_buffer(p, (2, self.n), torch.float64) for p in range(self.world)]
+        torch.cuda.synchronize()
+        self.hdl.barrier(channel=3, timeout_ms=self.TIMEOUT_MS)
+        torch.cuda.synchronize()
+
+    def barrier(self, channel):
+        self.hdl.barrier(channel=channel, timeout_ms=self.TIMEOUT_MS)
+
+    def all_reduce(self, t, slot, channel):
+        """t (n doubles, device) <- sum over ranks of t.  The slot is rewritten only after every rank has passed at
+        least one later barrier, i.e. after it has read this one."""
+        import torch
+        self.views[self.rank][slot].copy_(t)
+        self.barrier(channel)
+        torch.sum(torch.stack([v[slot] for v in self.views]), dim=0, out=t)
+
+
+_side_streams = {}
+
+
+def _side_stream(dev):
+    """One high-priority side stream per device for the overlapped reduce-scatter."""
+    import torch
+    if dev not in _side_streams:
+        _side_streams[dev] = (torch.cuda.Stream(device=dev, priority=-1), torch.zeros(1, dtype=torch.float32, device=dev))
+    return _side_streams[dev]
+
+
+def run_sharded_iterations_peer(engine, niter, group=None, materialize_last=True, overlap=True, sync=None):
     """User-sharded iterations with the item-side exchange over NVLink peer / NVSwitch multicast memory: each rank
     reduces its slice of item rows straight out of all ranks' partial-sum buffers, updates it, and stores the result
-    into every replica.  The only NCCL traffic is k-double all-reduces (Theta and Beta column sums), which double as
-    the cross-GPU barriers the kernels need.
+    into every replica.  Besides that kernel only k-double sums cross GPUs (Theta and Beta column sums), and they
+    double as the cross-GPU barriers the kernels need: NCCL all-reduces, or with `sync` (a SymmSync) device-side
+    barriers and peer reads over symmetric memory.
 
     overlap=True splits the exchange: the reduce-scatter half (hpf_reduce_items_peer) starts right after the
     item-major pass on a second stream -- behind one extra barrier that makes every rank's partial sums final -- and
@@ -200,22 +280,52 @@ def run_sharded_iterations_peer(engine, niter, group=None, materialize_last=True
     main = torch.cuda.current_stream()
     if overlap:
         side, t_bar = _side_stream(dev)
+    phases = _PhaseTimer() if (os.environ.get("HPF_PHASES") == "1" and not torch.cuda.is_current_stream_capturing()) else None
     for it in range(int(niter)):
         last = materialize_last and it == niter - 1
+        if phases:
+            phases.mark("start")
         engine.sweep_side(0)
+        if phases:
+            phases.mark("item-major pass")
         if overlap:
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                _all_reduce_device(t_bar, group)            # every rank's item-major pass is done
+                if sync is not None:                        # every rank's item-major pass is done
+                    sync.barrier(0)
+                else:
+                    _all_reduce_device(t_bar, group)
                 engine.reduce_items_peer(side.cuda_stream)
         engine.sweep_side(1)
+        if phases:
+            phases.mark("user-major pass")
         engine.update_users(last)
-        _all_reduce_device(t_theta, group)
+        if phases:
+            phases.mark("user update")
+        if sync is not None:
+            sync.all_reduce(t_theta, 0, 1)
+        else:
+            _all_reduce_device(t_theta, group)
+        if phases:
+            phases.mark("Theta column sums (barrier)")
         if overlap:
             main.wait_stream(side)
+        if phases:
+            phases.mark("wait for the reduce-scatter")
         engine.update_items_peer(last)
-        _all_reduce_device(t_beta, group)
+        if phases:
+            phases.mark("item update + broadcast")
+        if sync is not None:
+            sync.all_reduce(t_beta, 1, 2)
+        else:
+            _all_reduce_device(t_beta, group)
+        if phases:
+            phases.mark("Beta column sums (barrier)")
         engine.peer_finish()
+        if phases:
+            phases.mark("re-zero item sums")
+    if phases:
+        phases.report()
 
 
 class ShardedLoop:
@@ -257,6 +367,14 @@ class ShardedLoop:
         self.mode = mode
         #: reduce-scatter half of the fused exchange on a second stream, under the user-major pass (HPF_EXCHANGE_OVERLAP=0: off)
         self.overlap = (os.environ.get("HPF_EXCHANGE_OVERLAP", "1") != "0") if overlap is None else bool(overlap)
+        #: barriers and k-double sums over symmetric memory instead of NCCL (needs the symmetric allocation; HPF_SYNC=nccl: off)
+        self.sync = None
+        if self._symm is not None and os.environ.get("HPF_SYNC", "symm") == "symm":
+            try:
+                self.sync = SymmSync(engine.k, group)
+            except Exception as exc:
+                import warnings
+                warnings.warn("symmetric-memory barriers unavailable (%r): using NCCL all-reduces" % (exc,))
         self.use_graph = bool(graph) and self.world > 1
         self.stream = torch.cuda.Stream() if self.use_graph else torch.cuda.current_stream()
         self.graph = None
@@ -269,11 +387,19 @@ class ShardedLoop:
         if mode == "peer":
             attach_peers(engine, group)
 
+    def describe(self):
+        """exchange mode + how the ranks synchronise, for telemetry"""
+        if self.mode in ("nvls", "symm", "peer"):
+            return "%s%s, %s barriers" % (self.mode, ", reduce-scatter overlapped" if self.overlap else "",
+                                          "symmetric-memory" if self.sync is not None else "NCCL")
+        return self.mode
+
     def _iterations(self, n, materialize_last):
         if self.mode == "single":
             self.engine.step_full(n)
         elif self.mode in ("peer", "nvls", "symm"):
-            run_sharded_iterations_peer(self.engine, n, self.group, materialize_last=materialize_last, overlap=self.overlap)
+            run_sharded_iterations_peer(self.engine, n, self.group, materialize_last=materialize_last, overlap=self.overlap,
+                                        sync=self.sync)
         elif self.mode == "overlap":
             run_sharded_iterations_overlapped(self.engine, n, group=self.group)
         else:
@@ -311,6 +437,7 @@ class ShardedLoop:
     def close(self):
         """Call AFTER the engine is closed when symmetric memory is in use (the engine's item buffers live in it)."""
         self.graph = None
+        self.sync = None
         self._symm = None
 
 
@@ -345,6 +472,7 @@ def sharded_parity_check(local_device, options=None, nU=60_000, nI=25_000, nnz=1
     loop.run(its)
     torch.cuda.synchronize()
     mine = eng.export_all()
+    how = loop.describe()
     eng.close()
     loop.close()
     cdev = dev if dist.get_backend(group) == "nccl" else torch.device("cpu")
@@ -373,7 +501,7 @@ def sharded_parity_check(local_device, options=None, nU=60_000, nI=25_000, nnz=1
                     Beta=rel(mine["Beta"], single["Beta"]), Lambda_shp=rel(mine["Lambda_shp"], single["Lambda_shp"]),
                     Lambda_rte=rel(mine["Lambda_rte"], single["Lambda_rte"]), t_rte=rel(mine["t_rte"], single["t_rte"]))
         result = {"what": "%d fp64 iterations of %dx%dx%d k=%d sharded over %d GPUs (exchange=%s%s) vs one engine"
-                          % (its, nU, nI, nnz, k, world, loop.mode, ", graph replay" if graph else ""),
+                          % (its, nU, nI, nnz, k, world, how, ", graph replay" if graph else ""),
                   "max_rel_err": max(errs.values()), "errors": errs, "tolerance": 1e-10,
                   "item_replicas_bit_identical": bool(int(same.item()) == 1)}
         result["ok"] = bool(result["max_rel_err"] < 1e-10 and result["item_replicas_bit_identical"])

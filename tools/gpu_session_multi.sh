@@ -22,11 +22,13 @@ if has bench; then
 for MODE in ${BENCH_MODES:-nvls peer}; do
 for GRAPH in ${BENCH_GRAPH:-1 0}; do
 for OVL in ${BENCH_OVERLAP:-1 0}; do
-log "bench N=$N exchange=$MODE graph=$GRAPH overlap=$OVL"
-TAG=N${N}_${MODE}_g${GRAPH}_o$OVL
-HPF_MULTI=$MODE HPF_GRAPH=$GRAPH HPF_EXCHANGE_OVERLAP=$OVL timeout 300 $TR --master-port 29542 bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline ${BENCH_ARGS:-} \
+for SYNC in ${BENCH_SYNC:-symm nccl}; do
+log "bench N=$N exchange=$MODE graph=$GRAPH overlap=$OVL sync=$SYNC"
+TAG=N${N}_${MODE}_g${GRAPH}_o${OVL}_$SYNC
+HPF_SYNC=$SYNC HPF_MULTI=$MODE HPF_GRAPH=$GRAPH HPF_EXCHANGE_OVERLAP=$OVL timeout 300 $TR --master-port 29542 bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline ${BENCH_ARGS:-} \
     > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
-log "  rc=$? $(cut -c1-230 $OUT/bench_$TAG.json)"
+log "  rc=$? $(grep '^{' $OUT/bench_$TAG.json | cut -c1-230)"
+done
 done
 done
 done
