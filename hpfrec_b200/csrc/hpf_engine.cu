@@ -283,6 +283,7 @@ struct hpf_engine {
                                   // stride is the whole class width) or loaded straight into registers (0)
     int v_prefetch = 0;           // 1: L2 prefetch of the gathered rows two batches ahead (measurement variant)
     int v_fullrow = -1;           // copy whole row strides instead of zero-filling pad packs (-1 default = off)
+    int v_rs_ctas = 0;            // CTAs of the stand-alone reduce-scatter kernel (0 = default 48)
     int v_robust = -1;            // rescue path for underflowing normalisers: -1 auto (tiny shape priors), 0 off, 1 on
     bool robust_on = false;       // resolved from v_robust and (a, c) when a step starts
     void *dirU = nullptr, *dirI = nullptr;  // robust mode: phi sums that bypass the row factor (nU x ld, nI x ld)
@@ -896,6 +897,9 @@ int hpf_set_option(hpf_engine* h, const char* name, double value) {
         if (!strcmp(name, "fullrow")) h->v_fullrow = (int)value;
         if (!strcmp(name, "robust")) h->v_robust = (int)value;
         drop_graphs(h);
+    } else if (!strcmp(name, "rs_ctas")) {
+        if (value < 0 || value > 148 * 8) return fail(HPF_EINVAL, "rs_ctas out of range");
+        h->v_rs_ctas = (int)value;
     } else if (!strcmp(name, "strict")) {
         h->strict = (int)value;
     } else if (!strcmp(name, "use_graph")) {
@@ -1277,9 +1281,11 @@ int hpf_reduce_items_peer(hpf_engine* h, void* stream) {
         TRY(dispatch(h->rb, h->ld, [&](auto cfg) {
             using C = decltype(cfg);
             using real = typename C::real;
-            // NVLink-bound, and it shares the SMs with the user-major pass: two CTAs per SM at most
+            // NVLink-latency-bound, and it shares the SMs with the user-major pass (measured at 2 GPUs: 296 CTAs slowed
+            // that pass by 0.08-0.28 ms): a few CTAs, each thread keeping 4 rows' packs in flight
             int grid = row_grid(r1 - r0, C::lpg);
-            if (grid > 148 * 2) grid = 148 * 2;
+            const int cap = h->v_rs_ctas > 0 ? h->v_rs_ctas : 48;
+            if (grid > cap) grid = cap;
             if (h->peer_multicast)
                 hpf::reduce_items_peer_kernel<real, C::lpg, C::vpl, true><<<grid, 256, 0, st>>>(r0, r1, h->ld, h->k, h->peers);
             else

@@ -311,6 +311,8 @@ template <typename real, int LPG, int VPL, bool MC>
 __global__ void __launch_bounds__(256)
 reduce_items_peer_kernel(int r0, int r1, int ld, int k, PeerTable pt) {
     constexpr int EPV = Pack<real>::N;
+    constexpr int U = 4;  // rows per lane group per trip: the kernel runs on a FEW CTAs (it shares the SMs with the
+                          // user-major pass), so the loads in flight that fill NVLink have to come from each thread
     const int gl = (threadIdx.x & 31) % LPG;
     const int groups_per_block = blockDim.x / LPG;
     const int g0 = blockIdx.x * groups_per_block + threadIdx.x / LPG;
@@ -323,35 +325,46 @@ reduce_items_peer_kernel(int r0, int r1, int ld, int k, PeerTable pt) {
         off[v] = (gl + LPG * v) * EPV;
         act[v] = off[v] < k;
     }
-    for (int r = r0 + g0; r < r1; r += gstride) {
-        Pack<real> asum[VPL];
+    for (int rb = r0 + g0; rb < r1; rb += gstride * U) {
+        Pack<real> asum[U][VPL];
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) asum[v] = pack_zero<real>();
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) asum[u][v] = pack_zero<real>();
         if (MC) {
 #pragma unroll
-            for (int v = 0; v < VPL; ++v)
-                if (act[v]) asum[v] = mc_ld_reduce((const real*)pt.mc_acc + (size_t)r * ld + off[v]);
-        }
-        for (int p0 = 0; !MC && p0 < pt.world; p0 += 8) {
-            Pack<real> pv[VPL][8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const bool have = p0 + q < pt.world;
-                const real* base = (const real*)pt.acc[have ? p0 + q : pt.rank];
+            for (int u = 0; u < U; ++u) {
+                const int r = rb + u * gstride;
 #pragma unroll
                 for (int v = 0; v < VPL; ++v)
-                    pv[v][q] = (have && act[v]) ? ld_pack(base + (size_t)r * ld + off[v]) : pack_zero<real>();
+                    if (r < r1 && act[v]) asum[u][v] = mc_ld_reduce((const real*)pt.mc_acc + (size_t)r * ld + off[v]);
             }
+        } else {
+            for (int p = 0; p < pt.world; ++p) {  // fixed rank order, as in the fused kernel: identical bits everywhere
+                const real* base = (const real*)pt.acc[p];
+                Pack<real> pv[U][VPL];
 #pragma unroll
-            for (int q = 0; q < 8; ++q)  // the same fixed rank order as the fused kernel: identical bits
+                for (int u = 0; u < U; ++u) {
+                    const int r = rb + u * gstride;
 #pragma unroll
-                for (int v = 0; v < VPL; ++v)
+                    for (int v = 0; v < VPL; ++v)
+                        pv[u][v] = (r < r1 && act[v]) ? ld_pack(base + (size_t)r * ld + off[v]) : pack_zero<real>();
+                }
 #pragma unroll
-                    for (int e = 0; e < EPV; ++e) asum[v].v[e] += pv[v][q].v[e];
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v)
+#pragma unroll
+                        for (int e = 0; e < EPV; ++e) asum[u][v].v[e] += pv[u][v].v[e];
+            }
         }
 #pragma unroll
-        for (int v = 0; v < VPL; ++v)
-            if (act[v]) st_pack(mine + (size_t)r * ld + off[v], asum[v]);
+        for (int u = 0; u < U; ++u) {
+            const int r = rb + u * gstride;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v)
+                if (r < r1 && act[v]) st_pack(mine + (size_t)r * ld + off[v], asum[u][v]);
+        }
     }
 }
 
