@@ -44,13 +44,8 @@ __device__ __forceinline__ void st_pack(real* p, const Pack<real>& r) {
     *reinterpret_cast<int4*>(p) = *reinterpret_cast<const int4*>(&r);
 }
 
-// L2 residency control: the gathered factor panel is loaded with an evict_last policy, the
-// streamed triples with evict_first, so the stream does not push the panel out of the 126 MB L2.
-__device__ __forceinline__ uint64_t l2_policy_keep() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
+// L2 policies of the sweep's measurement variants (HINT template flag; measured neutral to harmful, off by default):
+// streamed triples / own rows / REDs evict_first, gathered rows evict_last for a fraction of the lines.
 __device__ __forceinline__ uint64_t l2_policy_stream() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
@@ -63,16 +58,6 @@ __device__ __forceinline__ Pack<real> ldg_pack_hint(const real* p, uint64_t pol)
     asm volatile("ld.global.nc.L2::cache_hint.v4.b32 {%0, %1, %2, %3}, [%4], %5;"
                  : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])
                  : "l"(p), "l"(pol));
-    return r;
-}
-// gathered rows are touched once per SM: do not let them displace anything in L1
-template <typename real>
-__device__ __forceinline__ Pack<real> ldg_pack_noalloc(const real* p) {
-    Pack<real> r;
-    uint32_t* w = reinterpret_cast<uint32_t*>(&r);
-    asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])
-                 : "l"(p));
     return r;
 }
 __device__ __forceinline__ int ldg_stream(const int* p, uint64_t pol) {
@@ -92,43 +77,9 @@ __device__ __forceinline__ double ldg_stream(const double* p, uint64_t pol) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// mbarrier + 1-D bulk async copy (TMA, SASS: UBLKCP / SYNCS) used by the staged-gather sweep
-// ---------------------------------------------------------------------------------------------
+// shared-memory address of a generic pointer, and a 128-bit shared-memory load
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_fence_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {
-    }
-}
-// global -> shared bulk copy of `bytes` (multiple of 16, both addresses 16-byte aligned); completion
-// is signalled on the mbarrier as transaction bytes
-__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
 }
 template <typename real>
 __device__ __forceinline__ Pack<real> lds_pack(uint32_t addr) {
@@ -138,23 +89,8 @@ __device__ __forceinline__ Pack<real> lds_pack(uint32_t addr) {
     return r;
 }
 
-// four consecutive triples with 128-bit loads (read-only path); all lanes of a group read the same address
-__device__ __forceinline__ void ldg4(const int* p, int (&v)[4]) {
-    const int4 q = __ldg(reinterpret_cast<const int4*>(p));
-    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-}
-__device__ __forceinline__ void ldg4(const float* p, float (&v)[4]) {
-    const float4 q = __ldg(reinterpret_cast<const float4*>(p));
-    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-}
-__device__ __forceinline__ void ldg4(const double* p, double (&v)[4]) {
-    const double2 a = __ldg(reinterpret_cast<const double2*>(p));
-    const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
-    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
-}
-
 // per-thread asynchronous 16-byte copy global -> shared (LDGSTS, L2-only caching) and its group fences:
-// the landing zone of the deep gather pipeline in sweep_major_v3_kernel
+// the landing zone of the gathered-row ring in sweep_rows_kernel
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 }
@@ -162,12 +98,6 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-template <typename real>
-__device__ __forceinline__ void sts_pack(uint32_t addr, const Pack<real>& r) {
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(&r);
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
 }
 
 // vector reduction into global memory: RED.E.ADD.F32x4 (sm_90+) for float, 2x RED.E.ADD.F64 for double
@@ -221,7 +151,7 @@ __device__ __forceinline__ double rexp(double x) { return exp(x); }
 __device__ __forceinline__ float rdiv_fast(float a, float b) { return __fdividef(a, b); }
 __device__ __forceinline__ double rdiv_fast(double a, double b) { return a / b; }
 
-// count / normaliser with a bare MUFU.RCP (1 ulp) and one multiply: the deep-pipeline sweep is issue-bound,
+// count / normaliser with a bare MUFU.RCP (1 ulp) and one multiply: the sweep spends its issue slots elsewhere,
 // and the normaliser is a sum of products of numbers in (0, 1] with at least one term equal to the
 // product of the two row maxima's neighbours -- far from the denormal range __fdividef guards against
 __device__ __forceinline__ float rdiv_rcp(float a, float b) {
