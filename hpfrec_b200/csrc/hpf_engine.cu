@@ -284,6 +284,10 @@ struct hpf_engine {
     int v_prefetch = 0;           // 1: L2 prefetch of the gathered rows two batches ahead (measurement variant)
     int v_fullrow = -1;           // copy whole row strides instead of zero-filling pad packs (-1 default = off)
     int v_rs_ctas = 0;            // CTAs of the stand-alone reduce-scatter kernel (0 = default 48)
+    int v_overlap_update = -1;    // user update under the item-major pass: -1 measured default, 0 off, N > 0 on with N CTAs
+    void* xu_alt = nullptr;       // second user-factor buffer for that overlap (the pass gathers the old one)
+    cudaStream_t side = nullptr;  // its stream
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int v_robust = -1;            // rescue path for underflowing normalisers: -1 auto (tiny shape priors), 0 off, 1 on
     bool robust_on = false;       // resolved from v_robust and (a, c) when a step starts
     void *dirU = nullptr, *dirI = nullptr;  // robust mode: phi sums that bypass the row factor (nU x ld, nI x ld)
@@ -523,14 +527,19 @@ int row_grid(int64_t nrows, int lpg) {
     return (int)want;
 }
 
+// x_out: where the new per-row factors go (nullptr = in place).  side_ctas > 0: the launch that runs UNDER a sweep
+// pass on h->side, as that many 128-thread CTAs (one per SM fits beside the pass's three CTAs).
 template <typename C>
-int launch_update_rows(hpf_engine* h, bool users, bool mat) {
+int launch_update_rows(hpf_engine* h, bool users, bool mat, void* x_out = nullptr, int side_ctas = 0) {
     using real = typename C::real;
     const int64_t n = users ? h->nU : h->nI;
     if (n == 0) return HPF_OK;
-    const int grid = row_grid(n, C::lpg);
+    const int block = side_ctas > 0 ? 128 : 256;
+    const int grid = side_ctas > 0 ? side_ctas : row_grid(n, C::lpg);
+    cudaStream_t st = side_ctas > 0 ? h->side : h->stream;
     const size_t smem = sizeof(double) * h->ld;
     real* x = (real*)(users ? h->xu : h->xi);
+    real* xo = x_out ? (real*)x_out : x;
     real* acc = (real*)(users ? h->accU : h->accI);
     real* shp = (real*)(users ? h->Gshp : h->Lshp);
     real* rte = (real*)(users ? h->Grte : h->Lrte);
@@ -542,11 +551,11 @@ int launch_update_rows(hpf_engine* h, bool users, bool mat) {
     const real add_rate = (real)(users ? h->add_k : h->add_t);
     real* direct = h->robust_on ? (real*)(users ? h->dirU : h->dirI) : nullptr;
     if (mat)
-        hpf::update_rows_kernel<real, C::lpg, C::vpl, true><<<grid, 256, smem, h->stream>>>(
-            (int)n, h->ld, h->k, x, acc, direct, shp, rte, rate, other, out, prior, shp_rate, add_rate);
+        hpf::update_rows_kernel<real, C::lpg, C::vpl, true><<<grid, block, smem, st>>>(
+            (int)n, h->ld, h->k, x, xo, acc, direct, shp, rte, rate, other, out, prior, shp_rate, add_rate);
     else
-        hpf::update_rows_kernel<real, C::lpg, C::vpl, false><<<grid, 256, smem, h->stream>>>(
-            (int)n, h->ld, h->k, x, acc, direct, shp, rte, rate, other, out, prior, shp_rate, add_rate);
+        hpf::update_rows_kernel<real, C::lpg, C::vpl, false><<<grid, block, smem, st>>>(
+            (int)n, h->ld, h->k, x, xo, acc, direct, shp, rte, rate, other, out, prior, shp_rate, add_rate);
     h->launches++;
     CKK();
     return HPF_OK;
@@ -644,8 +653,60 @@ int do_update(hpf_engine* h, bool users, bool mat) {
     });
 }
 
+// The user update only needs the user-major pass (and last iteration's Beta column sums), so it can run UNDER the
+// item-major pass: user-major pass -> { item-major pass on the main stream || user update on a second stream, writing the
+// new factors into a second buffer because the pass is still gathering the old ones } -> item update.  The update is
+// issue / DRAM bound, the pass is bound by the L1TEX data pipe, and one 128-thread update CTA fits beside the pass's
+// three CTAs on every SM.
+// Measured at H (profiles/r02_overlap_update.txt): 296 CTAs 2.26-2.28 ms per iteration against 2.36 sequential; 148 and
+// 222 leave the update as the long pole, 370-592 take too much from the pass; 64-thread CTAs and one row of look-ahead in
+// the update kernel were both slower.  Small problems keep the sequential order (the fork / join is not free).
+constexpr int kDefaultOverlapUpdate = 296;
+int overlap_update_ctas(hpf_engine* h) {
+    const int dflt = (h->nnz >= (1 << 22) && h->nU >= 100000) ? kDefaultOverlapUpdate : 0;
+    const int v = h->v_overlap_update >= 0 ? h->v_overlap_update : dflt;
+    if (v <= 0 || h->timing || h->robust_on || h->sweep_mode != 0 || h->nnz == 0 || h->nU == 0) return 0;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (h->stream != nullptr && h->stream != cudaStreamLegacy) cudaStreamIsCapturing(h->stream, &cap);
+    if (cap != cudaStreamCaptureStatusNone) return 0;  // a captured iteration would bake the buffer swap in
+    return v;
+}
+
+int one_iteration_overlapped(hpf_engine* h, bool mat, int ctas) {
+    if (!h->xu_alt) {
+        const size_t mu = h->mat_bytes(h->nU);
+        CK(hpf_malloc(&h->xu_alt, mu));
+        CK(cudaMemsetAsync(h->xu_alt, 0, mu, h->stream));  // pad packs are read by whole-stride copies and never written
+    }
+    if (!h->side) {
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, hi));
+        CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    }
+    TRY(do_sweep(h, 2));  // user-major pass
+    CK(cudaEventRecord(h->ev_fork, h->stream));
+    CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    CK(cudaMemsetAsync(h->Tsum, 0, sizeof(double) * h->ld, h->side));
+    TRY(dispatch(h->rb, h->ld, [&](auto cfg) {
+        using C = decltype(cfg);
+        return launch_update_rows<C>(h, true, mat, h->xu_alt, ctas);
+    }));
+    CK(cudaEventRecord(h->ev_join, h->side));
+    TRY(do_sweep(h, 1));  // item-major pass: gathers the OLD user factors
+    CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    void* t = h->xu;
+    h->xu = h->xu_alt;
+    h->xu_alt = t;
+    drop_graphs(h);  // a graph captured earlier holds the old buffer roles
+    TRY(do_update(h, false, mat));
+    return HPF_OK;
+}
+
 int one_iteration(hpf_engine* h, bool mat) {
     if (h->robust_on) mat = true;  // the rescue path recomputes E[log] from the materialised state
+    if (const int ctas = overlap_update_ctas(h)) return one_iteration_overlapped(h, mat, ctas);
     TRY(do_sweep(h));
     TRY(do_update(h, true, mat));
     mark(h, 3);
@@ -805,6 +866,10 @@ int hpf_destroy(hpf_engine* h) {
         for (void* p : shared) hpf_uncached_free(p);
         h->accI = h->xi = h->trte = h->Lshp = h->Lrte = nullptr;
     }
+    if (h->side) cudaStreamDestroy(h->side);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    hpf_free(h->xu_alt);
     void* ptrs[] = {h->Gshp, h->Grte, h->Lshp, h->Lrte, h->krte, h->trte, h->xu, h->xi, h->accU, h->accI, h->Tsum, h->Bsum, h->stamp_u, h->stamp_i,
                     h->bt_major, h->bt_minor, h->bt_cnt, h->bt_off, h->bt_ids, h->bt_val, h->bt_scan_tmp, h->dirU, h->dirI, h->ep_ids};
     for (void* p : ptrs) hpf_free(p);
@@ -896,6 +961,10 @@ int hpf_set_option(hpf_engine* h, const char* name, double value) {
         if (value != -1 && value != 0 && value != 1) return fail(HPF_EINVAL, "%s must be -1 (default), 0 or 1", name);
         if (!strcmp(name, "fullrow")) h->v_fullrow = (int)value;
         if (!strcmp(name, "robust")) h->v_robust = (int)value;
+        drop_graphs(h);
+    } else if (!strcmp(name, "overlap_update")) {
+        if (value < -1 || value > 148 * 16) return fail(HPF_EINVAL, "overlap_update out of range");
+        h->v_overlap_update = (int)value;
         drop_graphs(h);
     } else if (!strcmp(name, "rs_ctas")) {
         if (value < 0 || value > 148 * 8) return fail(HPF_EINVAL, "rs_ctas out of range");

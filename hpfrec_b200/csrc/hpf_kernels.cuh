@@ -20,14 +20,16 @@ namespace hpf {
 //   rte  = shp_rate / rate[r] + colsum_other[j]  pxi:236 (users) / pxi:255 (items)
 //   E[x] = shp / rte                             pxi:251 / 256  -> column sums (double) for the other side
 //   rate[r] = add_rate + sum_j E[x]              pxi:258 / 259
-//   x    = exp(psi(shp) - log(rte) - rowmax)     the per-row factor of next iteration's update_phi
+//   x    = exp(psi(shp) - log(rte) - rowmax)     the per-row factor of next iteration's update_phi; written to x_out,
+//                                                which is x itself, or a second buffer when the update runs UNDER the
+//                                                other side's pass, which is still gathering the old factors
 // MAT=true also stores shp and rte (needed for export / minibatch steps); lean iterations skip that.
 // `direct` (robust mode, else NULL): phi sums of the nnz the sweep's rescue path handled, added to the
 // shape as they are (not scaled by x) and re-zeroed.
 // =============================================================================================
 template <typename real, int LPG, int VPL, bool MAT>
 __global__ void __launch_bounds__(256)
-update_rows_kernel(int nrows, int ld, int k, real* __restrict__ x, real* __restrict__ acc, real* __restrict__ direct,
+update_rows_kernel(int nrows, int ld, int k, const real* x, real* x_out, real* __restrict__ acc, real* __restrict__ direct,
                    real* __restrict__ shp_out, real* __restrict__ rte_out, real* __restrict__ rate,
                    const double* __restrict__ colsum_other, double* __restrict__ colsum_out,
                    real prior, real shp_rate, real add_rate) {
@@ -97,7 +99,7 @@ update_rows_kernel(int nrows, int ld, int k, real* __restrict__ x, real* __restr
             Pack<real> xn;
 #pragma unroll
             for (int e = 0; e < EPV; ++e) xn.v[e] = (off[v] + e < k) ? rexp(E[v].v[e] - m) : real(0);
-            st_pack(x + (size_t)r * ld + off[v], xn);
+            st_pack(x_out + (size_t)r * ld + off[v], xn);
             st_pack(acc + (size_t)r * ld + off[v], pack_zero<real>());
             if (MAT) {
                 st_pack(shp_out + (size_t)r * ld + off[v], shp[v]);

@@ -513,3 +513,35 @@ def test_sweep_kernel_golden_trajectory(golden_full, lpg):
         out = _fit_gpu(g["Y"], g["ix_u"], g["ix_i"], 100, 100, 10, its, 123, lpg=lpg, chunk=32)
         for key in STATE_KEYS:
             assert relerr(out[key], g["it%d_%s" % (its, key)]) < tol, key
+
+
+@pytest.mark.parametrize("dtype,k,tol", [(np.float64, 10, 1e-12), (np.float32, 50, 3e-5), (np.float64, 50, 1e-12)])
+def test_user_update_under_the_item_pass_is_result_neutral(golden_full, dtype, k, tol):
+    """overlap_update: the user update on a second stream under the item-major pass, new factors into a second buffer
+    (the buffers swap roles every iteration).  Same iterations as the oracle, odd and even iteration counts, mixed with
+    lean / materialising calls and a minibatch step in between (which reads the CURRENT factor buffer)."""
+    g = golden_full
+    st0 = O.initialize_parameters(100, 100, k, 123, 0.3, 1.0, 0.3, 1.0, dtype)
+    ref = {k_: v.astype(np.float64) for k_, v in st0.items()}
+    eng = _engine_from(st0, k, dtype, overlap_update=148, chunk=64, panel_mb=0.01)
+    eng.set_hyper(HYP["a"], HYP["a_prime"], HYP["b_prime"], HYP["c"], HYP["c_prime"], HYP["d_prime"])
+    eng.load_coo(np.ascontiguousarray(g["ix_u"], np.int64), np.ascontiguousarray(g["ix_i"], np.int64),
+                 np.ascontiguousarray(g["Y"], dtype))
+    done = 0
+    for n in (1, 2, 3, 1):
+        eng.step_full(n)
+        for _ in range(n):
+            O.cavi_full_iteration(ref, g["Y"], g["ix_u"], g["ix_i"], **HYP)
+        done += n
+        out = eng.export_all()
+        for key in STATE_KEYS:
+            assert relerr(out[key], ref[key]) < tol, (key, done)
+    # the non-overlapped path continues from the same state
+    eng.set_option("overlap_update", 0)
+    eng.step_full(2)
+    for _ in range(2):
+        O.cavi_full_iteration(ref, g["Y"], g["ix_u"], g["ix_i"], **HYP)
+    out = eng.export_all()
+    for key in STATE_KEYS:
+        assert relerr(out[key], ref[key]) < tol, key
+    eng.close()
