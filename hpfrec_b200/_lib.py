@@ -33,6 +33,7 @@ SIGNATURES = {
     "hpf_update_users": ([_P], _c.c_int),
     "hpf_update_users_ex": ([_P, _c.c_int32], _c.c_int),
     "hpf_update_items": ([_P], _c.c_int),
+    "hpf_item_pass_with_user_update": ([_P, _I32], _c.c_int),
     "hpf_partials": ([_P, _c.POINTER(_P), _c.POINTER(_I64), _c.POINTER(_P), _c.POINTER(_I64)], _c.c_int),
     "hpf_peer_export": ([_P, _P], _c.c_int),
     "hpf_peer_attach": ([_P, _I32, _I32, _P], _c.c_int),

@@ -672,7 +672,8 @@ int overlap_update_ctas(hpf_engine* h) {
     return v;
 }
 
-int one_iteration_overlapped(hpf_engine* h, bool mat, int ctas) {
+// item-major pass on the main stream || user update on the second stream (new factors into xu_alt), then the swap
+int item_pass_with_user_update(hpf_engine* h, bool mat, int ctas) {
     if (!h->xu_alt) {
         const size_t mu = h->mat_bytes(h->nU);
         CK(hpf_malloc(&h->xu_alt, mu));
@@ -685,7 +686,6 @@ int one_iteration_overlapped(hpf_engine* h, bool mat, int ctas) {
         CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     }
-    TRY(do_sweep(h, 2));  // user-major pass
     CK(cudaEventRecord(h->ev_fork, h->stream));
     CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
     CK(cudaMemsetAsync(h->Tsum, 0, sizeof(double) * h->ld, h->side));
@@ -700,6 +700,12 @@ int one_iteration_overlapped(hpf_engine* h, bool mat, int ctas) {
     h->xu = h->xu_alt;
     h->xu_alt = t;
     drop_graphs(h);  // a graph captured earlier holds the old buffer roles
+    return HPF_OK;
+}
+
+int one_iteration_overlapped(hpf_engine* h, bool mat, int ctas) {
+    TRY(do_sweep(h, 2));  // user-major pass
+    TRY(item_pass_with_user_update(h, mat, ctas));
     TRY(do_update(h, false, mat));
     return HPF_OK;
 }
@@ -1134,6 +1140,21 @@ int hpf_update_users_ex(hpf_engine* h, int32_t materialize) {
     if (!h->x_valid) return fail(HPF_ESTATE, "hpf_update_users must follow hpf_sweep");
     DeviceGuard guard(h->device);
     return do_update(h, true, materialize != 0);
+}
+
+int hpf_item_pass_with_user_update(hpf_engine* h, int32_t materialize) {
+    if (!h) return fail(HPF_EINVAL, "engine is NULL");
+    if (!h->data_loaded) return fail(HPF_ESTATE, "no data loaded (call hpf_load_coo first)");
+    if (!h->x_valid) return fail(HPF_ESTATE, "hpf_item_pass_with_user_update must follow the user-major pass");
+    DeviceGuard guard(h->device);
+    TRY(resolve_robust(h));
+    if (h->robust_on) return fail(HPF_EINVAL, "robust mode (tiny shape priors) is not available for sharded sweeps");
+    const int ctas = h->v_overlap_update >= 0 ? h->v_overlap_update : kDefaultOverlapUpdate;
+    if (ctas <= 0 || h->nnz == 0 || h->nU == 0 || h->sweep_mode != 0) {  // sequential form of the same two steps
+        TRY(do_sweep(h, 1));
+        return do_update(h, true, materialize != 0);
+    }
+    return item_pass_with_user_update(h, materialize != 0, ctas);
 }
 
 int hpf_update_items(hpf_engine* h) {

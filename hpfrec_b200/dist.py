@@ -266,6 +266,9 @@ def run_sharded_iterations_peer(engine, niter, group=None, materialize_last=True
     double as the cross-GPU barriers the kernels need: NCCL all-reduces, or with `sync` (a SymmSync) device-side
     barriers and peer reads over symmetric memory.
 
+    overlap="update": user-major pass first, then the item-major pass with the USER UPDATE under it on the engine's
+    second stream (hpf_item_pass_with_user_update), then the single fused exchange kernel.  The engine's two user-factor
+    buffers swap roles every iteration, so a captured loop must hold an even number of iterations.
     overlap=True splits the exchange: the reduce-scatter half (hpf_reduce_items_peer) starts right after the
     item-major pass on a second stream -- behind one extra barrier that makes every rank's partial sums final -- and
     runs UNDER the user-major pass and the user update; the update + broadcast half follows on the main stream.
@@ -278,6 +281,9 @@ def run_sharded_iterations_peer(engine, niter, group=None, materialize_last=True
     t_theta = wrap_device_buffer(p_theta, n_theta, torch.float64, dev)
     t_beta = wrap_device_buffer(p_beta, n_beta, torch.float64, dev)
     main = torch.cuda.current_stream()
+    update_under_pass = overlap == "update"
+    if update_under_pass:
+        overlap = False
     if overlap:
         side, t_bar = _side_stream(dev)
     phases = _PhaseTimer() if (os.environ.get("HPF_PHASES") == "1" and not torch.cuda.is_current_stream_capturing()) else None
@@ -285,6 +291,34 @@ def run_sharded_iterations_peer(engine, niter, group=None, materialize_last=True
         last = materialize_last and it == niter - 1
         if phases:
             phases.mark("start")
+        if update_under_pass:
+            # user-major pass, then the item-major pass with the user update under it (engine's second stream); the
+            # Theta sums below are also the barrier that makes every rank's item-side partial sums final
+            engine.sweep_side(1)
+            if phases:
+                phases.mark("user-major pass")
+            engine.item_pass_with_user_update(last)
+            if phases:
+                phases.mark("item-major pass || user update")
+            if sync is not None:
+                sync.all_reduce(t_theta, 0, 1)
+            else:
+                _all_reduce_device(t_theta, group)
+            if phases:
+                phases.mark("Theta column sums (barrier)")
+            engine.update_items_peer(last)
+            if phases:
+                phases.mark("item update + exchange")
+            if sync is not None:
+                sync.all_reduce(t_beta, 1, 2)
+            else:
+                _all_reduce_device(t_beta, group)
+            if phases:
+                phases.mark("Beta column sums (barrier)")
+            engine.peer_finish()
+            if phases:
+                phases.mark("re-zero item sums")
+            continue
         engine.sweep_side(0)
         if phases:
             phases.mark("item-major pass")
@@ -343,6 +377,8 @@ class ShardedLoop:
           "auto"    "nvls" with NCCL, else "peer"
     Construct it BEFORE hpf_load_state (the fused modes map the engine's item-side buffers into every rank)."""
 
+    ITERATIONS_PER_REPLAY = 2   # with overlap="update" (the engine's user-factor buffers swap every iteration)
+
     def __init__(self, engine, mode="auto", group=None, graph=False, overlap=None):
         import torch
         import torch.distributed as dist
@@ -366,7 +402,10 @@ class ShardedLoop:
                 mode = "peer"
         self.mode = mode
         #: reduce-scatter half of the fused exchange on a second stream, under the user-major pass (HPF_EXCHANGE_OVERLAP=0: off)
-        self.overlap = (os.environ.get("HPF_EXCHANGE_OVERLAP", "1") != "0") if overlap is None else bool(overlap)
+        if overlap is None:
+            env = os.environ.get("HPF_EXCHANGE_OVERLAP", "1")
+            overlap = "update" if env == "update" else env != "0"
+        self.overlap = overlap
         #: barriers and k-double sums over symmetric memory instead of NCCL (needs the symmetric allocation; HPF_SYNC=nccl: off)
         self.sync = None
         if self._symm is not None and os.environ.get("HPF_SYNC", "symm") == "symm":
@@ -378,7 +417,8 @@ class ShardedLoop:
         self.use_graph = bool(graph) and self.world > 1
         self.stream = torch.cuda.Stream() if self.use_graph else torch.cuda.current_stream()
         self.graph = None
-        self.launches_per_replay = 0   # engine kernels inside one captured iteration
+        self._swaps = 0
+        self.launches_per_replay = 0   # engine kernels inside one captured replay
         self.replayed_launches = 0     # kernels launched through graph replays (the engine cannot count those)
         if self.use_graph:
             engine.set_stream(self.stream)
@@ -390,11 +430,14 @@ class ShardedLoop:
     def describe(self):
         """exchange mode + how the ranks synchronise, for telemetry"""
         if self.mode in ("nvls", "symm", "peer"):
-            return "%s%s, %s barriers" % (self.mode, ", reduce-scatter overlapped" if self.overlap else "",
+            how = {True: ", reduce-scatter overlapped", False: "", "update": ", user update under the item-major pass"}[self.overlap]
+            return "%s%s, %s barriers" % (self.mode, how,
                                           "symmetric-memory" if self.sync is not None else "NCCL")
         return self.mode
 
     def _iterations(self, n, materialize_last):
+        if self.overlap == "update":
+            self._swaps = (self._swaps + int(n)) % 2   # user-factor buffer roles relative to the captured graph
         if self.mode == "single":
             self.engine.step_full(n)
         elif self.mode in ("peer", "nvls", "symm"):
@@ -417,19 +460,30 @@ class ShardedLoop:
         cur = torch.cuda.current_stream()
         self.stream.wait_stream(cur)
         with torch.cuda.stream(self.stream):
-            if self.graph is None and niter > 1:
-                self._iterations(1, False)   # warm-up (NCCL channels, lazy allocations) before capture
-                niter -= 1
+            # a captured replay holds TWO iterations: the engine's user-factor buffers swap roles every iteration when the
+            # user update runs under the item-major pass, and a replay must leave them as it found them
+            per = self.ITERATIONS_PER_REPLAY if self.overlap == "update" else 1
+            if self.graph is None and niter > per + 1:
+                self._iterations(per, False)   # warm-up (NCCL channels, lazy allocations, second stream) before capture
+                niter -= per
                 self.stream.synchronize()
+                self._swaps = 0                # the graph's buffer roles are the ones that hold right now
                 g = torch.cuda.CUDAGraph()
                 before = self.engine.launch_count
                 with torch.cuda.graph(g, stream=self.stream, capture_error_mode="thread_local"):
-                    self._iterations(1, False)
+                    self._iterations(per, False)
                 self.launches_per_replay = self.engine.launch_count - before
                 self.graph = g
-            for _ in range(niter - 1):
+            while self.graph is not None and niter > per:
+                if self._swaps:   # an odd number of eager iterations since the capture: the graph's buffer roles do not hold
+                    self._iterations(1, False)
+                    niter -= 1
+                    continue
                 self.graph.replay()
                 self.replayed_launches += self.launches_per_replay
+                niter -= per
+            if niter > 1:
+                self._iterations(niter - 1, False)
             if niter >= 1:
                 self._iterations(1, True)
         cur.wait_stream(self.stream)
@@ -442,7 +496,7 @@ class ShardedLoop:
 
 
 def sharded_parity_check(local_device, options=None, nU=60_000, nI=25_000, nnz=1_500_000, k=50, its=3, mode=None,
-                         graph=False, group=None):
+                         graph=False, group=None, overlap=None):
     """Driver-visible proof of the multi-GPU data plane (run by bench.py before it times anything at N>1):
     `its` fp64 iterations of a down-scaled problem, user-sharded over all ranks with the SAME exchange the
     bench is about to time, against one engine on rank 0.  Checks (i) every state array <= 1e-10 relative,
@@ -466,7 +520,7 @@ def sharded_parity_check(local_device, options=None, nU=60_000, nI=25_000, nnz=1
     eng = Engine(hi - lo, nI, k, 8, local_device)
     for name, val in (options or {}).items():
         eng.set_option(name, val)
-    loop = ShardedLoop(eng, mode=mode, graph=graph, group=group)
+    loop = ShardedLoop(eng, mode=mode, graph=graph, group=group, overlap=overlap)
     eng.load_state(np.ascontiguousarray(Gs[lo:hi]), np.ascontiguousarray(Gr[lo:hi]), Ls, Lr, np.ascontiguousarray(kr[lo:hi]), tr)
     eng.load_coo(lu, li, ly)
     loop.run(its)

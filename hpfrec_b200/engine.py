@@ -168,6 +168,10 @@ class Engine:
     def update_users(self, materialize=True):
         _lib.check(self._lib.hpf_update_users_ex(self._h, int(bool(materialize))))
 
+    def item_pass_with_user_update(self, materialize=True):
+        """Item-major pass with the user update running under it on a second stream (after sweep_side(1))."""
+        _lib.check(self._lib.hpf_item_pass_with_user_update(self._h, int(bool(materialize))))
+
     def update_items(self):
         _lib.check(self._lib.hpf_update_items(self._h))
 

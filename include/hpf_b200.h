@@ -113,6 +113,12 @@ int hpf_update_users(hpf_engine* h);
  * iteration before an export must materialize. */
 int hpf_update_users_ex(hpf_engine* h, int32_t materialize);
 int hpf_update_items(hpf_engine* h);
+/* hpf_sweep_side(h, 0) + hpf_update_users_ex(h, materialize) as ONE step in which the user update runs UNDER the
+ * item-major pass on a second stream (it only needs the user-major pass, which the caller has already run with
+ * hpf_sweep_side(h, 1)); the new user factors go into a second buffer and the two buffers swap roles on return.  A
+ * caller that captures its loop into a CUDA graph must capture an EVEN number of iterations, so that a replay leaves
+ * the roles as it found them.  Falls back to the two steps in sequence when engine option overlap_update is 0. */
+int hpf_item_pass_with_user_update(hpf_engine* h, int32_t materialize);
 int hpf_partials(hpf_engine* h, void** item_sums, int64_t* item_sums_count, void** theta_colsum,
                  int64_t* theta_colsum_count);
 

@@ -29,14 +29,21 @@ def main():
     ok = True
     modes = os.environ.get("HPF_TEST_MODES", "peer,overlap,plain" if shared else "nvls,symm,peer,overlap,plain").split(",")
     for mode in modes:
-        for graph in ((False, True) if (not shared and mode in ("peer", "nvls")) else (False,)):
-            try:
-                res = hdist.sharded_parity_check(local, nU=20_000, nI=8_000, nnz=400_000, k=50, its=3, mode=mode, graph=graph)
-            except Exception as exc:  # a failed check must fail the test, not hang the other ranks
-                res = {"ok": False, "error": repr(exc)[:300], "what": "mode=%s graph=%s" % (mode, graph)}
-            if dist.get_rank() == 0:
-                print("PARITY " + json.dumps(res), flush=True)
-            ok = ok and bool(res.get("ok"))
+        fused = mode in ("peer", "nvls", "symm")
+        # the fused exchange in its three schedules: reduce-scatter under the user-major pass, user update under the
+        # item-major pass (the engine's factor buffers swap every iteration), nothing overlapped
+        for overlap in ((True, "update", False) if fused else (None,)):
+            for graph in ((False, True) if (not shared and mode in ("peer", "nvls")) else (False,)):
+                its = 7 if graph else 3   # a replay holds two iterations: 7 = warm-up, capture, replays, odd remainder
+                try:
+                    res = hdist.sharded_parity_check(local, nU=20_000, nI=8_000, nnz=400_000, k=50, its=its, mode=mode,
+                                                     graph=graph, overlap=overlap,
+                                                     options={"overlap_update": 96} if overlap == "update" else None)
+                except Exception as exc:  # a failed check must fail the test, not hang the other ranks
+                    res = {"ok": False, "error": repr(exc)[:300], "what": "mode=%s graph=%s overlap=%s" % (mode, graph, overlap)}
+                if dist.get_rank() == 0:
+                    print("PARITY " + json.dumps(res), flush=True)
+                ok = ok and bool(res.get("ok"))
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 
