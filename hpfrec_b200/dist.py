@@ -403,8 +403,15 @@ class ShardedLoop:
         self.mode = mode
         #: reduce-scatter half of the fused exchange on a second stream, under the user-major pass (HPF_EXCHANGE_OVERLAP=0: off)
         if overlap is None:
-            env = os.environ.get("HPF_EXCHANGE_OVERLAP", "1")
-            overlap = "update" if env == "update" else env != "0"
+            # measured (profiles/r02_bench_C5_N8_update.json, r02_bench_N2_overlap_*.json): hiding the user update pays
+            # once a rank owns a million users (C5 on 8 GPUs: 252 vs 242-244 it/s); below that the two schedules tie
+            # (H on 2 GPUs: 1.446 vs 1.441 ms) and the reduce-scatter overlap, the schedule every H number was
+            # measured with, stays
+            env = os.environ.get("HPF_EXCHANGE_OVERLAP", "auto")
+            if env == "auto":
+                overlap = "update" if engine.nU >= 1_000_000 else True
+            else:
+                overlap = "update" if env == "update" else env != "0"
         self.overlap = overlap
         #: barriers and k-double sums over symmetric memory instead of NCCL (needs the symmetric allocation; HPF_SYNC=nccl: off)
         self.sync = None
