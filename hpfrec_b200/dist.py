@@ -219,7 +219,7 @@ class SymmSync:
     and the two k-double column-sum exchanges as "publish my partial, barrier, add everybody's partials in rank
     order" (every rank adds the same numbers in the same order: bit-identical sums on all ranks)."""
 
-    TIMEOUT_MS = 20000   # a barrier that is not met traps instead of hanging the GPU
+    TIMEOUT_MS = 60000   # a barrier that is not met traps instead of hanging the GPU
 
     def __init__(self, n, group=None):
         import torch
