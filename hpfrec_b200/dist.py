@@ -403,13 +403,13 @@ class ShardedLoop:
         self.mode = mode
         #: reduce-scatter half of the fused exchange on a second stream, under the user-major pass (HPF_EXCHANGE_OVERLAP=0: off)
         if overlap is None:
-            # measured (profiles/r02_bench_C5_N8_update.json, r02_bench_N2_overlap_*.json): hiding the user update pays
-            # once a rank owns a million users (C5 on 8 GPUs: 252 vs 242-244 it/s); below that the two schedules tie
-            # (H on 2 GPUs: 1.446 vs 1.441 ms) and the reduce-scatter overlap, the schedule every H number was
-            # measured with, stays
+            # measured (profiles/r02_bench_C5_N8_update.json, r02_bench_N8_schedule_*.json, r02_bench_N2_overlap_*.json):
+            # hiding the user update wins on C5 at 8 GPUs (252 vs 242-244 it/s) and on H at 8 GPUs (1462 vs 1441 on the
+            # same box) and ties on H at 2 GPUs (1.446 vs 1.441 ms); tiny shards keep the reduce-scatter overlap (the
+            # update is too short to be worth a second stream there)
             env = os.environ.get("HPF_EXCHANGE_OVERLAP", "auto")
             if env == "auto":
-                overlap = "update" if engine.nU >= 1_000_000 else True
+                overlap = "update" if engine.nU >= 100_000 else True
             else:
                 overlap = "update" if env == "update" else env != "0"
         self.overlap = overlap
