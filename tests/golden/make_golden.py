@@ -126,7 +126,7 @@ def main():
     print("golden files written to", OUT, "|", ver)
 
 
-if __name__ == "__main__" and "--api" not in sys.argv:
+if __name__ == "__main__" and "--api" not in sys.argv and "--foldin" not in sys.argv:
     main()
 
 
@@ -224,5 +224,39 @@ def api_golden():
     print("toy_api.npz written")
 
 
+def foldin_golden():
+    """Fold-in of MANY new users through the reference's own predict_factors (hpfrec/__init__.py:989-1058 ->
+    calc_user_factors, pxi:476-520), one call per user as the reference does it: the golden for
+    HPF.predict_factors_batch.  Two stopping thresholds: the default, and a loose one that stops users at different
+    iterations."""
+    import warnings
+    import pandas as pd
+    HPF = load_reference_class()
+    df = O.readme_toy()
+    warnings.simplefilter("ignore")
+    m = HPF(k=8, use_float=False, random_seed=7, maxiter=100, verbose=False, ncores=1, stop_crit="train-llk",
+            check_every=5, stop_thr=1e-3, reindex=False)
+    m.fit(df.copy())
+    rng = np.random.default_rng(5)
+    users, items, counts = [], [], []
+    for u in range(30):
+        n = int(rng.integers(1, 30))
+        it = rng.choice(100, size=n, replace=False)
+        users.append(np.full(n, u)); items.append(it); counts.append(rng.integers(1, 6, size=n).astype(float))
+    users, items, counts = np.concatenate(users), np.concatenate(items), np.concatenate(counts)
+    out = {"versions": versions(), "fit_Theta": m.Theta, "users": users, "items": items, "counts": counts}
+    for tag, thr in (("default", 1e-3), ("loose", 3e-2)):
+        th = np.empty((30, 8))
+        for u in range(30):
+            sel = users == u
+            th[u] = m.predict_factors(pd.DataFrame({"ItemId": items[sel], "Count": counts[sel]}), maxiter=10,
+                                      random_seed=1, stop_thr=thr)
+        out["theta_" + tag] = th
+    np.savez_compressed(os.path.join(OUT, "toy_foldin.npz"), **out)
+    print("toy_foldin.npz written")
+
+
 if __name__ == "__main__" and "--api" in sys.argv:
     api_golden()
+if __name__ == "__main__" and "--foldin" in sys.argv:
+    foldin_golden()
