@@ -345,7 +345,8 @@ def run_ours(a):
     # ---- multi-GPU: prove the sharded data plane before timing it -----------------------------------
     parity = None
     if world > 1 and not a.no_parity_check:
-        parity = hdist.sharded_parity_check(local, options=options)
+        # the same exchange, schedule and synchronisation the timed run below resolves to (per-rank share of the users)
+        parity = hdist.sharded_parity_check(local, options=options, overlap=hdist.resolve_overlap(nU // world))
 
     # ---- synthetic inputs, identical on every rank; each rank keeps its user range ---------------
     u, i, y = synth_coo_torch(nU, nI, nnz, dev, seed=42, alpha=a.alpha)

@@ -362,6 +362,19 @@ def run_sharded_iterations_peer(engine, niter, group=None, materialize_last=True
         phases.report()
 
 
+def resolve_overlap(n_users_local):
+    """The exchange schedule of the fused modes for a shard of `n_users_local` users: HPF_EXCHANGE_OVERLAP =
+    auto | 1 (reduce-scatter under the user-major pass) | update (user update under the item-major pass) | 0.
+    auto, measured (profiles/r02_bench_C5_N8_update.json, r02_bench_N8_schedule_*.json, r02_bench_N2_overlap_*.json):
+    hiding the user update wins on C5 at 8 GPUs (252 vs 242-244 it/s) and on H at 8 GPUs (1462 vs 1441 on the same
+    box) and ties on H at 2 GPUs (1.446 vs 1.441 ms); tiny shards keep the reduce-scatter overlap (the update is too
+    short to be worth a second stream there)."""
+    env = os.environ.get("HPF_EXCHANGE_OVERLAP", "auto")
+    if env == "auto":
+        return "update" if n_users_local >= 100_000 else True
+    return "update" if env == "update" else env != "0"
+
+
 class ShardedLoop:
     """Iteration driver of one user shard: picks the item-side exchange and, optionally, replays one captured
     iteration as a CUDA graph (kernels + collectives) so that the per-iteration host cost is a single graph
@@ -403,15 +416,7 @@ class ShardedLoop:
         self.mode = mode
         #: reduce-scatter half of the fused exchange on a second stream, under the user-major pass (HPF_EXCHANGE_OVERLAP=0: off)
         if overlap is None:
-            # measured (profiles/r02_bench_C5_N8_update.json, r02_bench_N8_schedule_*.json, r02_bench_N2_overlap_*.json):
-            # hiding the user update wins on C5 at 8 GPUs (252 vs 242-244 it/s) and on H at 8 GPUs (1462 vs 1441 on the
-            # same box) and ties on H at 2 GPUs (1.446 vs 1.441 ms); tiny shards keep the reduce-scatter overlap (the
-            # update is too short to be worth a second stream there)
-            env = os.environ.get("HPF_EXCHANGE_OVERLAP", "auto")
-            if env == "auto":
-                overlap = "update" if engine.nU >= 100_000 else True
-            else:
-                overlap = "update" if env == "update" else env != "0"
+            overlap = resolve_overlap(engine.nU)
         self.overlap = overlap
         #: barriers and k-double sums over symmetric memory instead of NCCL (needs the symmetric allocation; HPF_SYNC=nccl: off)
         self.sync = None
