@@ -137,3 +137,14 @@ def test_shard_triples_localises_user_ids():
     y = np.array([1., 2., 3., 4., 5.])
     lu, li, ly = hdist.shard_triples(u, i, y, 4, 10)
     assert lu.tolist() == [1, 5, 1] and li.tolist() == [2, 3, 4] and ly.tolist() == [2., 3., 4.]
+
+
+def test_resolve_overlap_schedule(monkeypatch):
+    """Exchange schedule of the fused modes: auto by shard size, explicit values of HPF_EXCHANGE_OVERLAP."""
+    from hpfrec_b200.dist import resolve_overlap
+    monkeypatch.delenv("HPF_EXCHANGE_OVERLAP", raising=False)
+    assert resolve_overlap(125_000) == "update" and resolve_overlap(1_250_000) == "update"
+    assert resolve_overlap(15_000) is True
+    for env, want in (("1", True), ("0", False), ("update", "update"), ("auto", True)):
+        monkeypatch.setenv("HPF_EXCHANGE_OVERLAP", env)
+        assert resolve_overlap(15_000) == want
