@@ -1450,11 +1450,15 @@ int hpf_describe(hpf_engine* h, char* buf, int64_t n) {
         minb = 2;
     }
     const int hint = h->v_hint >= 0 ? h->v_hint : kDefaultHint;
+    // CTAs of the user update that runs under the item-major pass in hpf_step_full (0 = the two run in sequence)
+    int ovu = h->v_overlap_update >= 0 ? h->v_overlap_update : ((h->nnz >= (1 << 22) && h->nU >= 100000) ? kDefaultOverlapUpdate : 0);
+    if (robust || h->sweep_mode != 0) ovu = 0;
     snprintf(buf, (size_t)n,
              "real_bytes=%d k=%d kw=%d ld=%d sweep=%d kernel=%s lpg=%d depth=%d block=%d minb=%d smem_gather=%d hint=%d fullrow=%d robust=%d chunk=%d "
-             "panel_mb=%g panels_user_major=%d panels_item_major=%d launches_per_iteration=%d",
+             "panel_mb=%g panels_user_major=%d panels_item_major=%d launches_per_iteration=%d overlap_update=%d",
              h->rb, h->k, h->kw, h->ld, h->sweep_mode, h->sweep_mode == 1 ? "sweep_coo_kernel" : "sweep_rows_kernel", lpg,
-             depth, block, minb, smem_gather, hint, fullrow, robust, h->chunk, h->panel_mb, h->panelsA, h->panelsB, h->sweep_mode == 0 ? 4 : 3);
+             depth, block, minb, smem_gather, hint, fullrow, robust, h->chunk, h->panel_mb, h->panelsA, h->panelsB, h->sweep_mode == 0 ? 4 : 3,
+             ovu);
     return HPF_OK;
 }
 
